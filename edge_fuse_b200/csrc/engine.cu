@@ -1,0 +1,547 @@
+// engine.cu — host side of the B200 cachemap engine: HBM layout, batch pipelines, C ABI.
+//
+// HBM layout per engine (one engine per GPU):
+//   key table   (slots+2) x 64 B          replaces the 32 LMDB environments (filemap.c:54-90)
+//   arena       bump-allocated records    {24-byte data_prefix, LZ4 block | raw page}
+//   page ring   2 x max_batch x bsize     double-buffered landing zone for host pages
+//   stage       max_batch x (bsize+1024)  encoder output before it is packed into the arena
+// A put batch is: H2D copy (copy stream)  ->  k_upsert  ->  k_encode (fingerprint + LZ4 + arena
+// commit + table publish), sub-batch k+1's copy overlapping sub-batch k's kernels.
+// A get batch is: k_lookup -> k_decode -> D2H copy.
+#include <mutex>
+#include <new>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include "../../include/cachemap_b200.h"
+#include "kernels.h"
+#include "common.cuh"
+#include "streamgen.cuh"
+
+static thread_local char g_err[512];
+
+void cmb_set_error(const char *what, cudaError_t e, const char *file, int line) {
+	snprintf(g_err, sizeof(g_err), "%s:%d: %s: %s", file, line, what, cudaGetErrorString(e));
+}
+static void set_error_msg(const char *msg) { snprintf(g_err, sizeof(g_err), "%s", msg); }
+
+using namespace cmb;
+
+struct cmb200_engine {
+	int device = 0;
+	int pshift = 16;
+	uint32_t bsize = 65536;
+	int accel = 12;
+	uint64_t capacity = 0;
+	uint32_t max_batch = 4096;
+	uint32_t flags = 0;
+	cudaStream_t st = nullptr, copy = nullptr;
+	cudaEvent_t landed[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr};
+	TableView table{};
+	ArenaView arena{};
+	unsigned long long *d_counters = nullptr;   // entries, tombs, head, garbage, dropped
+	uint8_t *d_pages[2] = {nullptr, nullptr};
+	uint8_t *d_stage = nullptr;
+	uint64_t stage_stride = 0;
+	unsigned long long *d_addr = nullptr, *d_ts = nullptr;
+	uint8_t *d_valid = nullptr;
+	uint32_t *d_slot = nullptr, *d_vlen = nullptr;
+	int32_t *d_lens = nullptr, *d_status = nullptr;
+	uint64_t *d_fps = nullptr, *d_recoff = nullptr;
+	unsigned int *d_work = nullptr;
+	unsigned long long seq = 1;
+	std::mutex mu;
+	cmb200_stats stats{};
+};
+
+#define ENG_CHECK(expr)                                                 \
+	do {                                                            \
+		cudaError_t e_ = (expr);                                \
+		if (e_ != cudaSuccess) {                                \
+			cmb_set_error(#expr, e_, __FILE__, __LINE__);   \
+			goto fail;                                      \
+		}                                                       \
+	} while (0)
+
+static uint64_t next_pow2(uint64_t v) {
+	uint64_t p = 1;
+	while (p < v) p <<= 1;
+	return p;
+}
+
+extern "C" const char *cmb200_last_error(void) { return g_err; }
+
+extern "C" int cmb200_device_count(void) {
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess) { cmb_set_error("cudaGetDeviceCount", e, __FILE__, __LINE__); return 0; }
+	return n;
+}
+
+static int select_device(int device) {
+	if (device >= 0) CMB_CHECK(cudaSetDevice(device));
+	int n = 0;
+	CMB_CHECK(cudaGetDeviceCount(&n));
+	if (n == 0) { set_error_msg("no CUDA device"); return -1; }
+	return 0;
+}
+
+extern "C" void cmb200_engine_destroy(cmb200_engine *e) {
+	if (!e) return;
+	cudaSetDevice(e->device);
+	if (e->st) cudaStreamSynchronize(e->st);
+	if (e->copy) cudaStreamSynchronize(e->copy);
+	cudaFree(e->table.slots); cudaFree(e->table.fp); cudaFree(e->arena.base); cudaFree(e->d_counters);
+	cudaFree(e->d_pages[0]); cudaFree(e->d_pages[1]); cudaFree(e->d_stage);
+	cudaFree(e->d_addr); cudaFree(e->d_ts); cudaFree(e->d_valid); cudaFree(e->d_slot); cudaFree(e->d_vlen);
+	cudaFree(e->d_lens); cudaFree(e->d_status); cudaFree(e->d_fps); cudaFree(e->d_recoff); cudaFree(e->d_work);
+	for (int i = 0; i < 2; i++) {
+		if (e->landed[i]) cudaEventDestroy(e->landed[i]);
+		if (e->consumed[i]) cudaEventDestroy(e->consumed[i]);
+	}
+	if (e->st) cudaStreamDestroy(e->st);
+	if (e->copy) cudaStreamDestroy(e->copy);
+	delete e;
+}
+
+extern "C" cmb200_engine *cmb200_engine_create(const cmb200_config *cfg) {
+	if (!cfg || cfg->pshift < 6 || cfg->pshift > 20) { set_error_msg("bad config: pshift must be 6..20"); return nullptr; }
+	if (select_device(cfg->device) != 0) return nullptr;
+	cmb200_engine *e = new (std::nothrow) cmb200_engine();
+	if (!e) return nullptr;
+	cudaGetDevice(&e->device);
+	e->pshift = cfg->pshift;
+	e->bsize = 1u << cfg->pshift;
+	e->accel = cfg->accel < 0 ? 1 : (cfg->accel > (1 << 20) ? (1 << 20) : cfg->accel);   // lz4.c:740
+	e->capacity = cfg->capacity;
+	e->max_batch = cfg->max_batch ? cfg->max_batch : 4096;
+	e->flags = cfg->flags;
+	const uint64_t B = e->max_batch;
+	{
+		uint64_t slots = cfg->table_slots ? next_pow2(cfg->table_slots) : next_pow2(2 * (cfg->capacity ? cfg->capacity : 1024));
+		if (slots < 1024) slots = 1024;
+		const char *cap_env = getenv("CMB200_MAX_TABLE_SLOTS");
+		uint64_t max_slots = cap_env ? next_pow2(strtoull(cap_env, nullptr, 0)) : (1ull << 27);
+		if (slots > max_slots) slots = max_slots;
+		e->table.cap = slots;
+		ENG_CHECK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
+		ENG_CHECK(cudaStreamCreateWithFlags(&e->copy, cudaStreamNonBlocking));
+		for (int i = 0; i < 2; i++) {
+			ENG_CHECK(cudaEventCreateWithFlags(&e->landed[i], cudaEventDisableTiming));
+			ENG_CHECK(cudaEventCreateWithFlags(&e->consumed[i], cudaEventDisableTiming));
+		}
+		ENG_CHECK(cudaMalloc(&e->table.slots, (slots + 2) * sizeof(Slot)));
+		ENG_CHECK(cudaMemsetAsync(e->table.slots, 0, (slots + 2) * sizeof(Slot), e->st));
+		if (e->flags & CMB200_FINGERPRINT) {
+			ENG_CHECK(cudaMalloc(&e->table.fp, (slots + 2) * 16));
+			ENG_CHECK(cudaMemsetAsync(e->table.fp, 0, (slots + 2) * 16, e->st));
+		}
+		ENG_CHECK(cudaMalloc(&e->d_counters, 8 * sizeof(unsigned long long)));
+		ENG_CHECK(cudaMemsetAsync(e->d_counters, 0, 8 * sizeof(unsigned long long), e->st));
+		e->table.entries = e->d_counters + 0;
+		e->table.tombs = e->d_counters + 1;
+		e->arena.head = e->d_counters + 2;
+		e->arena.garbage = e->d_counters + 3;
+		e->arena.dropped = e->d_counters + 4;
+
+		e->stage_stride = ((uint64_t)e->bsize + 1024 + 15) & ~15ull;        // filemap.c:120 dest[bsize+1024]
+		ENG_CHECK(cudaMalloc(&e->d_pages[0], B * e->bsize + 256));
+		ENG_CHECK(cudaMalloc(&e->d_pages[1], B * e->bsize + 256));
+		ENG_CHECK(cudaMalloc(&e->d_stage, B * e->stage_stride + 256));
+		ENG_CHECK(cudaMalloc(&e->d_addr, B * 16));
+		ENG_CHECK(cudaMalloc(&e->d_ts, B * 8));
+		ENG_CHECK(cudaMalloc(&e->d_valid, B));
+		ENG_CHECK(cudaMalloc(&e->d_slot, B * 4));
+		ENG_CHECK(cudaMalloc(&e->d_vlen, B * 4));
+		ENG_CHECK(cudaMalloc(&e->d_lens, B * 4));
+		ENG_CHECK(cudaMalloc(&e->d_status, B * 4));
+		ENG_CHECK(cudaMalloc(&e->d_fps, B * 16));
+		ENG_CHECK(cudaMalloc(&e->d_recoff, B * 8));
+		ENG_CHECK(cudaMalloc(&e->d_work, 64));
+
+		uint64_t arena = cfg->arena_bytes;
+		if (!arena) {
+			size_t free_b = 0, total_b = 0;
+			ENG_CHECK(cudaMemGetInfo(&free_b, &total_b));
+			uint64_t want = (cfg->capacity ? cfg->capacity : 1024) * (e->stage_stride + 32);
+			uint64_t lim = (uint64_t)(free_b * 0.8);
+			arena = want < lim ? want : lim;
+		}
+		arena = (arena + 255) & ~255ull;
+		ENG_CHECK(cudaMalloc(&e->arena.base, arena + 256));
+		e->arena.size = arena;
+		ENG_CHECK(cudaStreamSynchronize(e->st));
+	}
+	return e;
+fail:
+	cmb200_engine_destroy(e);
+	return nullptr;
+}
+
+extern "C" void *cmb200_host_alloc(size_t bytes) {
+	void *p = nullptr;
+	cudaError_t er = cudaMallocHost(&p, bytes);
+	if (er != cudaSuccess) { cmb_set_error("cudaMallocHost", er, __FILE__, __LINE__); return nullptr; }
+	return p;
+}
+extern "C" void cmb200_host_free(void *p) { if (p) cudaFreeHost(p); }
+extern "C" void *cmb200_dev_alloc(cmb200_engine *e, size_t bytes) {
+	void *p = nullptr;
+	if (e) cudaSetDevice(e->device);
+	cudaError_t er = cudaMalloc(&p, bytes + 256);
+	if (er != cudaSuccess) { cmb_set_error("cudaMalloc", er, __FILE__, __LINE__); return nullptr; }
+	return p;
+}
+extern "C" void cmb200_dev_free(cmb200_engine *e, void *p) { if (e) cudaSetDevice(e->device); if (p) cudaFree(p); }
+extern "C" int cmb200_memcpy_h2d(cmb200_engine *e, void *dev, const void *host, size_t bytes) {
+	cudaSetDevice(e->device);
+	CMB_CHECK(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, e->st));
+	CMB_CHECK(cudaStreamSynchronize(e->st));
+	return 0;
+}
+extern "C" int cmb200_memcpy_d2h(cmb200_engine *e, void *host, const void *dev, size_t bytes) {
+	cudaSetDevice(e->device);
+	CMB_CHECK(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, e->st));
+	CMB_CHECK(cudaStreamSynchronize(e->st));
+	return 0;
+}
+extern "C" void *cmb200_stream(cmb200_engine *e) { return (void *)e->st; }
+extern "C" int cmb200_sync(cmb200_engine *e) {
+	cudaSetDevice(e->device);
+	CMB_CHECK(cudaStreamSynchronize(e->copy));
+	CMB_CHECK(cudaStreamSynchronize(e->st));
+	return 0;
+}
+
+// ---- put ---------------------------------------------------------------------------------
+
+static int put_impl(cmb200_engine *e, size_t n, const cmb200_addr *addr, const uint8_t *valid,
+    const uint8_t *pages, bool pages_on_dev, const uint64_t *ts, int32_t *lens_out) {
+	std::lock_guard<std::mutex> g(e->mu);
+	CMB_CHECK(cudaSetDevice(e->device));
+	const size_t B = e->max_batch;
+	size_t nb = 0;
+	for (size_t at = 0; at < n; at += B, nb++) {
+		const uint32_t m = (uint32_t)((n - at < B) ? n - at : B);
+		const int buf = (int)(nb & 1);
+		const uint8_t *d_in;
+		if (pages_on_dev) {
+			d_in = pages + at * e->bsize;
+		} else {
+			// land the pages in ring buffer `buf` once the kernels that last read it are done
+			CMB_CHECK(cudaStreamWaitEvent(e->copy, e->consumed[buf], 0));
+			CMB_CHECK(cudaMemcpyAsync(e->d_pages[buf], pages + at * e->bsize, (size_t)m * e->bsize,
+			    cudaMemcpyHostToDevice, e->copy));
+			CMB_CHECK(cudaEventRecord(e->landed[buf], e->copy));
+			CMB_CHECK(cudaStreamWaitEvent(e->st, e->landed[buf], 0));
+			d_in = e->d_pages[buf];
+		}
+		// The small per-chunk arrays ride the compute stream; the previous sub-batch's kernels
+		// are ordered before them, so the single set of device arrays is safe to reuse.
+		CMB_CHECK(cudaMemcpyAsync(e->d_addr, addr + at, (size_t)m * 16, cudaMemcpyHostToDevice, e->st));
+		if (valid) CMB_CHECK(cudaMemcpyAsync(e->d_valid, valid + at, m, cudaMemcpyHostToDevice, e->st));
+		if (ts) CMB_CHECK(cudaMemcpyAsync(e->d_ts, ts + at, (size_t)m * 8, cudaMemcpyHostToDevice, e->st));
+		if (launch_upsert(e->table, e->d_addr, valid ? e->d_valid : nullptr, m, e->seq, e->d_slot, e->st)) return -1;
+		EncodeJob job{};
+		job.pages = d_in; job.page_stride = e->bsize; job.nbytes = e->bsize; job.n = m;
+		job.accel = (uint32_t)e->accel;
+		job.stage = e->d_stage; job.stage_stride = e->stage_stride;
+		job.lens = e->d_lens;
+		job.fps = (e->flags & CMB200_FINGERPRINT) ? e->d_fps : nullptr;
+		job.work = e->d_work;
+		job.slot_idx = e->d_slot;
+		job.addr = e->d_addr;
+		job.ts = ts ? e->d_ts : nullptr;
+		job.seq0 = e->seq;
+		job.table = e->table; job.arena = e->arena;
+		if (launch_encode(job, e->st)) return -1;
+		if (!pages_on_dev) CMB_CHECK(cudaEventRecord(e->consumed[buf], e->st));
+		if (lens_out) CMB_CHECK(cudaMemcpyAsync(lens_out + at, e->d_lens, (size_t)m * 4, cudaMemcpyDeviceToHost, e->st));
+		e->seq += m;
+		e->stats.kernel_launches += 2;
+		// addr/valid/ts host arrays of the NEXT sub-batch are copied with cudaMemcpyAsync from
+		// pageable memory, which returns only after staging: no lifetime issue for the caller.
+	}
+	CMB_CHECK(cudaStreamSynchronize(e->st));
+	e->stats.put_chunks += n;
+	return 0;
+}
+
+extern "C" int cmb200_put_batch(cmb200_engine *e, size_t n, const cmb200_addr *addr, const uint8_t *valid,
+    const void *pages_host, const uint64_t *ts, int32_t *lens_out) {
+	return put_impl(e, n, addr, valid, (const uint8_t *)pages_host, false, ts, lens_out);
+}
+extern "C" int cmb200_put_batch_dev(cmb200_engine *e, size_t n, const cmb200_addr *addr, const uint8_t *valid,
+    const void *pages_dev, const uint64_t *ts, int32_t *lens_out) {
+	return put_impl(e, n, addr, valid, (const uint8_t *)pages_dev, true, ts, lens_out);
+}
+
+// ---- get ---------------------------------------------------------------------------------
+
+static int get_impl(cmb200_engine *e, size_t n, const cmb200_addr *addr, const uint8_t *valid,
+    uint8_t *pages_out, bool out_on_dev, int32_t *status_out) {
+	std::lock_guard<std::mutex> g(e->mu);
+	CMB_CHECK(cudaSetDevice(e->device));
+	const size_t B = e->max_batch;
+	size_t nb = 0;
+	for (size_t at = 0; at < n; at += B, nb++) {
+		const uint32_t m = (uint32_t)((n - at < B) ? n - at : B);
+		const int buf = (int)(nb & 1);
+		uint8_t *d_out = out_on_dev ? pages_out + at * e->bsize : e->d_pages[buf];
+		if (!out_on_dev) CMB_CHECK(cudaStreamWaitEvent(e->st, e->consumed[buf], 0));   // D2H of buf finished
+		CMB_CHECK(cudaMemcpyAsync(e->d_addr, addr + at, (size_t)m * 16, cudaMemcpyHostToDevice, e->st));
+		if (valid) CMB_CHECK(cudaMemcpyAsync(e->d_valid, valid + at, m, cudaMemcpyHostToDevice, e->st));
+		if (launch_lookup(e->table, e->d_addr, valid ? e->d_valid : nullptr, m, e->d_status, e->d_recoff,
+			e->d_vlen, nullptr, e->st)) return -1;
+		DecodeJob job{};
+		job.n = m; job.nbytes = e->bsize; job.pages = d_out; job.status = e->d_status;
+		job.rec_off = e->d_recoff; job.vlen = e->d_vlen; job.arena = e->arena.base;
+		if (launch_decode(job, e->st)) return -1;
+		CMB_CHECK(cudaMemcpyAsync(status_out + at, e->d_status, (size_t)m * 4, cudaMemcpyDeviceToHost, e->st));
+		if (!out_on_dev) {
+			CMB_CHECK(cudaEventRecord(e->landed[buf], e->st));
+			CMB_CHECK(cudaStreamWaitEvent(e->copy, e->landed[buf], 0));
+			CMB_CHECK(cudaMemcpyAsync(pages_out + at * e->bsize, d_out, (size_t)m * e->bsize,
+			    cudaMemcpyDeviceToHost, e->copy));
+			CMB_CHECK(cudaEventRecord(e->consumed[buf], e->copy));
+		}
+		e->stats.kernel_launches += 2;
+	}
+	CMB_CHECK(cudaStreamSynchronize(e->st));
+	CMB_CHECK(cudaStreamSynchronize(e->copy));
+	for (size_t i = 0; i < n; i++) {
+		if (status_out[i] != CMB200_INVALID) e->stats.get_requests++;
+		if (status_out[i] == CMB200_HIT) e->stats.get_hits++;
+	}
+	return 0;
+}
+
+extern "C" int cmb200_get_batch(cmb200_engine *e, size_t n, const cmb200_addr *addr, const uint8_t *valid,
+    void *pages_out_host, int32_t *status_out) {
+	return get_impl(e, n, addr, valid, (uint8_t *)pages_out_host, false, status_out);
+}
+extern "C" int cmb200_get_batch_dev(cmb200_engine *e, size_t n, const cmb200_addr *addr, const uint8_t *valid,
+    void *pages_out_dev, int32_t *status_out) {
+	return get_impl(e, n, addr, valid, (uint8_t *)pages_out_dev, true, status_out);
+}
+
+// ---- unset / entries / sample / records ----------------------------------------------------
+
+extern "C" int cmb200_unset_batch(cmb200_engine *e, size_t n, const cmb200_addr *addr) {
+	std::lock_guard<std::mutex> g(e->mu);
+	CMB_CHECK(cudaSetDevice(e->device));
+	for (size_t at = 0; at < n; at += e->max_batch) {
+		uint32_t m = (uint32_t)((n - at < e->max_batch) ? n - at : e->max_batch);
+		CMB_CHECK(cudaMemcpyAsync(e->d_addr, addr + at, (size_t)m * 16, cudaMemcpyHostToDevice, e->st));
+		if (launch_unset(e->table, e->arena, e->d_addr, m, e->st)) return -1;
+		e->stats.kernel_launches++;
+	}
+	CMB_CHECK(cudaStreamSynchronize(e->st));
+	return 0;
+}
+
+static int read_counters(cmb200_engine *e, unsigned long long out[8]) {
+	CMB_CHECK(cudaSetDevice(e->device));
+	CMB_CHECK(cudaMemcpyAsync(out, e->d_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->st));
+	CMB_CHECK(cudaStreamSynchronize(e->st));
+	return 0;
+}
+
+extern "C" uint64_t cmb200_entries(cmb200_engine *e) {
+	std::lock_guard<std::mutex> g(e->mu);
+	unsigned long long c[8];
+	if (read_counters(e, c)) return 0;
+	return c[0];
+}
+
+extern "C" int cmb200_get_stats(cmb200_engine *e, cmb200_stats *out) {
+	std::lock_guard<std::mutex> g(e->mu);
+	unsigned long long c[8];
+	if (read_counters(e, c)) return -1;
+	*out = e->stats;
+	out->entries = c[0]; out->tombstones = c[1]; out->arena_used = c[2]; out->arena_garbage = c[3];
+	out->dropped_puts = c[4];
+	out->table_slots = e->table.cap; out->arena_bytes = e->arena.size;
+	return 0;
+}
+
+extern "C" int cmb200_sample(cmb200_engine *e, size_t n, const uint64_t *r, cmb200_addr *addr_out,
+    uint64_t *ts_out, int32_t *ok_out) {
+	std::lock_guard<std::mutex> g(e->mu);
+	CMB_CHECK(cudaSetDevice(e->device));
+	if (n > e->max_batch) { set_error_msg("cmb200_sample: n exceeds max_batch"); return -1; }
+	uint32_t m = (uint32_t)n;
+	CMB_CHECK(cudaMemcpyAsync(e->d_recoff, r, n * 8, cudaMemcpyHostToDevice, e->st));
+	if (launch_sample(e->table, (const unsigned long long *)e->d_recoff, m, e->d_addr, e->d_ts, e->d_status, e->st)) return -1;
+	CMB_CHECK(cudaMemcpyAsync(addr_out, e->d_addr, n * 16, cudaMemcpyDeviceToHost, e->st));
+	CMB_CHECK(cudaMemcpyAsync(ts_out, e->d_ts, n * 8, cudaMemcpyDeviceToHost, e->st));
+	CMB_CHECK(cudaMemcpyAsync(ok_out, e->d_status, n * 4, cudaMemcpyDeviceToHost, e->st));
+	CMB_CHECK(cudaStreamSynchronize(e->st));
+	e->stats.kernel_launches++;
+	return 0;
+}
+
+extern "C" int cmb200_read_records(cmb200_engine *e, size_t n, const cmb200_addr *addr, void *out_host,
+    size_t stride, int32_t *len_out) {
+	std::lock_guard<std::mutex> g(e->mu);
+	CMB_CHECK(cudaSetDevice(e->device));
+	std::vector<int32_t> st(e->max_batch);
+	std::vector<uint64_t> off(e->max_batch);
+	std::vector<uint32_t> vl(e->max_batch);
+	for (size_t at = 0; at < n; at += e->max_batch) {
+		uint32_t m = (uint32_t)((n - at < e->max_batch) ? n - at : e->max_batch);
+		CMB_CHECK(cudaMemcpyAsync(e->d_addr, addr + at, (size_t)m * 16, cudaMemcpyHostToDevice, e->st));
+		if (launch_lookup(e->table, e->d_addr, nullptr, m, e->d_status, e->d_recoff, e->d_vlen, nullptr, e->st)) return -1;
+		CMB_CHECK(cudaMemcpyAsync(st.data(), e->d_status, m * 4, cudaMemcpyDeviceToHost, e->st));
+		CMB_CHECK(cudaMemcpyAsync(off.data(), e->d_recoff, m * 8, cudaMemcpyDeviceToHost, e->st));
+		CMB_CHECK(cudaMemcpyAsync(vl.data(), e->d_vlen, m * 4, cudaMemcpyDeviceToHost, e->st));
+		CMB_CHECK(cudaStreamSynchronize(e->st));
+		for (uint32_t i = 0; i < m; i++) {
+			if (st[i] != ST_HIT) { len_out[at + i] = -1; continue; }
+			uint32_t clen = vl[i] - 1;
+			size_t total = 24 + (clen ? clen : e->bsize);
+			if (total > stride) { set_error_msg("cmb200_read_records: stride too small"); return -1; }
+			CMB_CHECK(cudaMemcpyAsync((uint8_t *)out_host + (at + i) * stride, e->arena.base + off[i], total,
+			    cudaMemcpyDeviceToHost, e->st));
+			len_out[at + i] = (int32_t)total;
+		}
+		CMB_CHECK(cudaStreamSynchronize(e->st));
+	}
+	return 0;
+}
+
+extern "C" int cmb200_read_fingerprints(cmb200_engine *e, size_t n, const cmb200_addr *addr, uint64_t *fp_out,
+    int32_t *ok_out) {
+	std::lock_guard<std::mutex> g(e->mu);
+	CMB_CHECK(cudaSetDevice(e->device));
+	if (!e->table.fp) { set_error_msg("engine created without CMB200_FINGERPRINT"); return -1; }
+	for (size_t at = 0; at < n; at += e->max_batch) {
+		uint32_t m = (uint32_t)((n - at < e->max_batch) ? n - at : e->max_batch);
+		CMB_CHECK(cudaMemcpyAsync(e->d_addr, addr + at, (size_t)m * 16, cudaMemcpyHostToDevice, e->st));
+		if (launch_read_fp(e->table, e->d_addr, m, e->d_fps, e->d_status, e->st)) return -1;
+		CMB_CHECK(cudaMemcpyAsync(fp_out + 2 * at, e->d_fps, (size_t)m * 16, cudaMemcpyDeviceToHost, e->st));
+		CMB_CHECK(cudaMemcpyAsync(ok_out + at, e->d_status, (size_t)m * 4, cudaMemcpyDeviceToHost, e->st));
+		CMB_CHECK(cudaStreamSynchronize(e->st));
+	}
+	return 0;
+}
+
+// ---- kernel-level entry points -------------------------------------------------------------
+
+struct DevBuf {
+	void *p = nullptr;
+	~DevBuf() { if (p) cudaFree(p); }
+	int alloc(size_t bytes) { CMB_CHECK(cudaMalloc(&p, bytes + 256)); return 0; }
+	template <class T> T *as() { return (T *)p; }
+};
+
+extern "C" int cmb200_compose_keys(int device, size_t n, const uint64_t *offset, const uint64_t *nhid,
+    const uint32_t *genid, int pshift, cmb200_addr *addr_out, uint8_t *valid_out, uint64_t *key_out) {
+	if (select_device(device)) return -1;
+	DevBuf d_off, d_nh, d_g, d_addr, d_valid, d_key;
+	if (d_off.alloc(n * 8) || d_nh.alloc(n * 8) || d_g.alloc(n * 4) || d_addr.alloc(n * 16) || d_valid.alloc(n) || d_key.alloc(n * 8)) return -1;
+	CMB_CHECK(cudaMemcpy(d_off.p, offset, n * 8, cudaMemcpyHostToDevice));
+	CMB_CHECK(cudaMemcpy(d_nh.p, nhid, n * 8, cudaMemcpyHostToDevice));
+	CMB_CHECK(cudaMemcpy(d_g.p, genid, n * 4, cudaMemcpyHostToDevice));
+	if (launch_compose(d_off.as<uint64_t>(), d_nh.as<uint64_t>(), d_g.as<uint32_t>(), pshift, (uint32_t)n,
+		d_addr.as<unsigned long long>(), d_valid.as<uint8_t>(), d_key.as<unsigned long long>(), 0)) return -1;
+	CMB_CHECK(cudaMemcpy(addr_out, d_addr.p, n * 16, cudaMemcpyDeviceToHost));
+	CMB_CHECK(cudaMemcpy(valid_out, d_valid.p, n, cudaMemcpyDeviceToHost));
+	CMB_CHECK(cudaMemcpy(key_out, d_key.p, n * 8, cudaMemcpyDeviceToHost));
+	return 0;
+}
+
+extern "C" int cmb200_lz4_encode_batch(int device, const void *pages_host, size_t n, uint32_t nbytes,
+    size_t stride, int accel, void *blocks_out_host, size_t out_stride, int32_t *lens_out, uint64_t *fp_out) {
+	if (select_device(device)) return -1;
+	if (stride % 16 || stride < nbytes) { set_error_msg("encode_batch: stride must be a multiple of 16 and >= nbytes"); return -1; }
+	size_t bound = (size_t)nbytes + nbytes / 255 + 16;
+	size_t sstride = (bound + 15) & ~(size_t)15;
+	if (out_stride < bound) { set_error_msg("encode_batch: out_stride below LZ4_compressBound"); return -1; }
+	DevBuf d_in, d_stage, d_lens, d_fps, d_work;
+	if (d_in.alloc(n * stride) || d_stage.alloc(n * sstride) || d_lens.alloc(n * 4) || d_fps.alloc(n * 16) || d_work.alloc(64)) return -1;
+	CMB_CHECK(cudaMemcpy(d_in.p, pages_host, n * stride, cudaMemcpyHostToDevice));
+	EncodeJob job{};
+	job.pages = d_in.as<uint8_t>(); job.page_stride = stride; job.nbytes = nbytes; job.n = (uint32_t)n;
+	job.accel = accel < 0 ? 1u : (uint32_t)(accel > (1 << 20) ? (1 << 20) : accel);
+	if (accel == 0) job.accel = 1;   // LZ4_compress_fast(accel<1) -> 1 (lz4.c:740); raw mode is a store-level notion
+	job.stage = d_stage.as<uint8_t>(); job.stage_stride = sstride;
+	job.lens = d_lens.as<int32_t>();
+	job.fps = fp_out ? d_fps.as<uint64_t>() : nullptr;
+	job.work = d_work.as<unsigned int>();
+	if (launch_encode(job, 0)) return -1;
+	CMB_CHECK(cudaMemcpy(lens_out, d_lens.p, n * 4, cudaMemcpyDeviceToHost));
+	if (fp_out) CMB_CHECK(cudaMemcpy(fp_out, d_fps.p, n * 16, cudaMemcpyDeviceToHost));
+	CMB_CHECK(cudaMemcpy2D(blocks_out_host, out_stride, d_stage.p, sstride, bound < out_stride ? bound : out_stride, n,
+	    cudaMemcpyDeviceToHost));
+	return 0;
+}
+
+extern "C" int cmb200_lz4_decode_batch(int device, const void *blocks_host, size_t in_stride, const int32_t *lens,
+    size_t n, uint32_t nbytes, void *pages_out_host, int32_t *consumed_out) {
+	if (select_device(device)) return -1;
+	DevBuf d_blk, d_lens, d_out, d_used;
+	if (d_blk.alloc(n * in_stride) || d_lens.alloc(n * 4) || d_out.alloc(n * (size_t)nbytes) || d_used.alloc(n * 4)) return -1;
+	CMB_CHECK(cudaMemcpy(d_blk.p, blocks_host, n * in_stride, cudaMemcpyHostToDevice));
+	CMB_CHECK(cudaMemcpy(d_lens.p, lens, n * 4, cudaMemcpyHostToDevice));
+	CMB_CHECK(cudaMemset(d_out.p, 0, n * (size_t)nbytes));
+	DecodeJob job{};
+	job.n = (uint32_t)n; job.nbytes = nbytes; job.pages = d_out.as<uint8_t>(); job.status = d_used.as<int32_t>();
+	job.blocks = d_blk.as<uint8_t>(); job.block_stride = in_stride; job.lens = d_lens.as<int32_t>();
+	if (launch_decode(job, 0)) return -1;
+	CMB_CHECK(cudaMemcpy(consumed_out, d_used.p, n * 4, cudaMemcpyDeviceToHost));
+	CMB_CHECK(cudaMemcpy(pages_out_host, d_out.p, n * (size_t)nbytes, cudaMemcpyDeviceToHost));
+	return 0;
+}
+
+extern "C" int cmb200_fingerprint_batch(int device, const void *pages_host, size_t n, uint32_t nbytes,
+    size_t stride, uint64_t *fp_out) {
+	if (select_device(device)) return -1;
+	if (stride % 16) { set_error_msg("fingerprint_batch: stride must be a multiple of 16"); return -1; }
+	DevBuf d_in, d_fps;
+	if (d_in.alloc(n * stride) || d_fps.alloc(n * 16)) return -1;
+	CMB_CHECK(cudaMemcpy(d_in.p, pages_host, n * stride, cudaMemcpyHostToDevice));
+	if (launch_fingerprint(d_in.as<uint8_t>(), stride, nbytes, (uint32_t)n, d_fps.as<uint64_t>(), 0)) return -1;
+	CMB_CHECK(cudaMemcpy(fp_out, d_fps.p, n * 16, cudaMemcpyDeviceToHost));
+	return 0;
+}
+
+// ---- synthetic streams -----------------------------------------------------------------------
+
+extern "C" void cmb200_gen_chunk_host(uint64_t seed, uint64_t cid, uint32_t bsize, void *out) {
+	uint64_t *w = (uint64_t *)out;
+	for (uint32_t i = 0; i < bsize / 8; i++) w[i] = sg_chunk_word(seed, cid, bsize, i);
+}
+
+extern "C" int cmb200_gen_chunks_dev(cmb200_engine *e, uint64_t seed, const uint64_t *cids_host, size_t n, void *out_dev) {
+	std::lock_guard<std::mutex> g(e->mu);
+	CMB_CHECK(cudaSetDevice(e->device));
+	DevBuf d_c;
+	if (d_c.alloc(n * 8)) return -1;
+	CMB_CHECK(cudaMemcpyAsync(d_c.p, cids_host, n * 8, cudaMemcpyHostToDevice, e->st));
+	if (launch_streamgen(d_c.as<uint64_t>(), (uint32_t)n, seed, e->bsize, (uint8_t *)out_dev, e->st)) return -1;
+	CMB_CHECK(cudaStreamSynchronize(e->st));
+	return 0;
+}
+
+extern "C" uint64_t cmb200_gen_stream_ids(uint64_t seed2, size_t n, double dup, uint64_t first_cid, uint64_t *cid_out) {
+	uint64_t state = seed2, distinct = 0;
+	for (size_t k = 0; k < n; k++) {
+		state += SG_GOLDEN;
+		uint64_t r = sg_mix(state);
+		bool repeat = distinct > 0 && (double)(r >> 11) * (1.0 / 9007199254740992.0) < dup;
+		if (repeat) {
+			state += SG_GOLDEN;
+			cid_out[k] = first_cid + sg_mix(state) % distinct;
+		} else {
+			cid_out[k] = first_cid + distinct++;
+		}
+	}
+	return distinct;
+}
+
+extern "C" void cmb200_gen_addr(uint64_t seed, uint64_t cid, int pshift, uint64_t *offset_out, uint64_t *nhid_out) {
+	*offset_out = sg_offset(cid, pshift);
+	*nhid_out = sg_nhid(seed, cid);
+}

@@ -1,0 +1,439 @@
+// kernels.cu — sm_100a kernels of the cachemap hot path and their launchers.
+//
+//   k_encode      fingerprint + LZ4 block encode + arena commit, one warp per chunk  (HBM: §4)
+//   k_decode      table record -> LZ4 decode -> page, one warp per request
+//   k_fingerprint EF128 alone
+//   k_compose / k_upsert / k_lookup / k_unset / k_sample   the HBM key table
+//   k_streamgen   synthetic benchmark input
+#include <stdio.h>
+#include <stdlib.h>
+#include "kernels.h"
+#include "common.cuh"
+#include "fingerprint.cuh"
+#include "lz4_encode.cuh"
+#include "lz4_decode.cuh"
+#include "streamgen.cuh"
+
+namespace cmb {
+
+// ------------------------------------------------------------------------------------------
+// key table primitives
+// ------------------------------------------------------------------------------------------
+
+// FNV-1a-64 over the 16 in-memory bytes of {u,l} (cachemap/uint128.h:6-21, filemap.c:18-24).
+__host__ __device__ __forceinline__ unsigned long long fnv_addr(unsigned long long u, unsigned long long l) {
+	unsigned long long h = 14695981039346656037ULL;
+#pragma unroll
+	for (int i = 0; i < 8; i++) { h = (h ^ ((u >> (8 * i)) & 0xFF)) * 0x100000001b3ULL; }
+#pragma unroll
+	for (int i = 0; i < 8; i++) { h = (h ^ ((l >> (8 * i)) & 0xFF)) * 0x100000001b3ULL; }
+	return h;
+}
+
+// Home slot: the low bits of an FNV key are its weakest, so remix before masking.
+__device__ __forceinline__ uint64_t home_slot(unsigned long long key, uint64_t cap) {
+	unsigned long long z = key;
+	z = (z ^ (z >> 32)) * 0xD6E8FEB86659FD93ULL;
+	z ^= z >> 32;
+	return z & (cap - 1);
+}
+
+__device__ __forceinline__ unsigned long long ld_key(const Slot *s) {
+	return *reinterpret_cast<const volatile unsigned long long *>(&s->key);
+}
+
+// Finds the slot holding `key`, claiming a fresh one if absent.  Returns cap-relative index, or
+// 0xffffffff when the table is full.
+__device__ uint32_t table_find_or_claim(const TableView &t, unsigned long long key) {
+	if (key == KEY_EMPTY) return (uint32_t)t.cap;
+	if (key == KEY_TOMB) return (uint32_t)t.cap + 1;
+	uint64_t i = home_slot(key, t.cap);
+	for (uint64_t n = 0; n < t.cap; n++, i = (i + 1) & (t.cap - 1)) {
+		unsigned long long cur = ld_key(&t.slots[i]);
+		if (cur == key) return (uint32_t)i;
+		if (cur == KEY_EMPTY) {
+			unsigned long long old = atomicCAS(&t.slots[i].key, KEY_EMPTY, key);
+			if (old == KEY_EMPTY || old == key) return (uint32_t)i;
+		}
+	}
+	return 0xffffffffu;
+}
+
+__device__ uint32_t table_find(const TableView &t, unsigned long long key) {
+	if (key == KEY_EMPTY) return (uint32_t)t.cap;
+	if (key == KEY_TOMB) return (uint32_t)t.cap + 1;
+	uint64_t i = home_slot(key, t.cap);
+	for (uint64_t n = 0; n < t.cap; n++, i = (i + 1) & (t.cap - 1)) {
+		unsigned long long cur = ld_key(&t.slots[i]);
+		if (cur == key) return (uint32_t)i;
+		if (cur == KEY_EMPTY) break;
+	}
+	return 0xffffffffu;
+}
+
+// cachemap/cachemap.c:151-166 + filemap.c:18-24, one thread per request.
+__global__ void k_compose(const uint64_t *offset, const uint64_t *nhid, const uint32_t *genid, int pshift,
+    uint32_t n, unsigned long long *addr, uint8_t *valid, unsigned long long *key) {
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	unsigned long long page = offset[i] >> pshift;
+	bool ok = (page >> 44) == 0;
+	unsigned long long l = page | ((unsigned long long)genid[i] << 44);
+	unsigned long long u = nhid[i];
+	addr[2 * i] = u;
+	addr[2 * i + 1] = l;
+	valid[i] = ok;
+	if (key) key[i] = fnv_addr(u, l);
+}
+
+// Claims the slot of every chunk of a put batch and records stream order: the chunk with the
+// highest sequence per key is the one whose record survives (sequential last-writer-wins,
+// SURVEY.md App. B rule 4).
+__global__ void k_upsert(TableView t, const unsigned long long *addr, const uint8_t *valid, uint32_t n,
+    unsigned long long seq0, uint32_t *slot_idx) {
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	uint32_t idx = 0xffffffffu;
+	if (!valid || valid[i]) {
+		unsigned long long key = fnv_addr(addr[2 * i], addr[2 * i + 1]);
+		idx = table_find_or_claim(t, key);
+		if (idx != 0xffffffffu) atomicMax(&t.slots[idx].seq, seq0 + i);
+	}
+	slot_idx[i] = idx;
+}
+
+__global__ void k_lookup(TableView t, const unsigned long long *addr, const uint8_t *valid, uint32_t n,
+    int32_t *status, uint64_t *rec_off, uint32_t *vlen, unsigned long long *ts_out) {
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	int32_t st = ST_MISS;
+	uint64_t off = 0;
+	uint32_t vl = 0;
+	unsigned long long ts = 0;
+	if (valid && !valid[i]) {
+		st = ST_INVALID;
+	} else {
+		unsigned long long u = addr[2 * i], l = addr[2 * i + 1];
+		uint32_t idx = table_find(t, fnv_addr(u, l));
+		if (idx != 0xffffffffu) {
+			const Slot &s = t.slots[idx];
+			if (s.vlen != 0) {
+				if (s.addr_u == u && s.addr_l == l) {
+					st = ST_HIT; off = s.rec_off; vl = s.vlen; ts = s.ts;
+				} else {
+					st = ST_BAD_ENTRY;
+				}
+			}
+		}
+	}
+	status[i] = st;
+	if (rec_off) rec_off[i] = off;
+	if (vlen) vlen[i] = vl;
+	if (ts_out) ts_out[i] = ts;
+}
+
+// filemap_unset (filemap.c:188-215): delete by key, whatever address the record holds.
+__global__ void k_unset(TableView t, ArenaView a, const unsigned long long *addr, uint32_t n) {
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	uint32_t idx = table_find(t, fnv_addr(addr[2 * i], addr[2 * i + 1]));
+	if (idx == 0xffffffffu) return;
+	Slot &s = t.slots[idx];
+	// Two requests of one batch may name the same key: let exactly one retire the record.
+	uint32_t old = atomicExch(&s.vlen, 0u);
+	if (old == 0) return;
+	atomicAdd(t.entries, (unsigned long long)-1ll);
+	atomicAdd(a.garbage, (unsigned long long)s.alloc);
+	s.alloc = 0;
+	if (idx < t.cap) {
+		s.key = KEY_TOMB;
+		atomicAdd(t.tombs, 1ull);
+	}
+}
+
+__global__ void k_sample(TableView t, const unsigned long long *r, uint32_t n, unsigned long long *addr_out,
+    unsigned long long *ts_out, int32_t *ok) {
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	uint64_t start = home_slot(r[i], t.cap);
+	int32_t found = 0;
+	for (uint64_t k = 0; k < t.cap + 2; k++) {
+		uint64_t j = (start + k) % (t.cap + 2);
+		const Slot &s = t.slots[j];
+		if (s.vlen != 0) {
+			addr_out[2 * i] = s.addr_u; addr_out[2 * i + 1] = s.addr_l; ts_out[i] = s.ts;
+			found = 1;
+			break;
+		}
+	}
+	ok[i] = found;
+}
+
+// ------------------------------------------------------------------------------------------
+// fused fingerprint -> LZ4 encode -> arena commit
+// ------------------------------------------------------------------------------------------
+
+// Stores the finished block as a filemap record {data_prefix, block} (filemap.c:140-147) and
+// publishes it in the key table.  Called by the whole warp; lane 0 owns the bookkeeping.
+__device__ void commit_record(const EncodeJob &job, uint32_t i, uint32_t idx, const uint8_t *payload,
+    uint32_t plen, int32_t clen, bool payload_ro, uint64_t fp_hi, uint64_t fp_lo, int lane) {
+	Slot &s = job.table.slots[idx];
+	const uint32_t need = (24u + plen + 15u) & ~15u;
+	unsigned long long off = 0;
+	int ok = 1;
+	if (lane == 0) {
+		if (s.alloc >= need) {
+			off = s.rec_off;                         // rewrite in place
+		} else {
+			if (s.alloc) atomicAdd(job.arena.garbage, (unsigned long long)s.alloc);
+			off = atomicAdd(job.arena.head, (unsigned long long)need);
+			if (off + need > job.arena.size) {
+				// arena full: the put is dropped silently, as a full LMDB map drops it
+				// (filemap.c:143-145,154-157).
+				atomicAdd(job.arena.head, (unsigned long long)-(long long)need);
+				atomicAdd(job.arena.dropped, 1ull);
+				if (s.vlen) atomicAdd(job.table.entries, (unsigned long long)-1ll);
+				s.vlen = 0; s.alloc = 0;
+				ok = 0;
+			} else {
+				s.alloc = need; s.rec_off = off;
+			}
+		}
+	}
+	ok = __shfl_sync(CMB_FULL, ok, 0);
+	if (!ok) return;
+	off = __shfl_sync(CMB_FULL, off, 0);
+	uint8_t *rec = job.arena.base + off;
+	const unsigned long long au = job.addr[2 * i], al = job.addr[2 * i + 1];
+	if (lane < 6) {
+		uint32_t w;
+		switch (lane) {
+		case 0: w = (uint32_t)au; break;
+		case 1: w = (uint32_t)(au >> 32); break;
+		case 2: w = (uint32_t)al; break;
+		case 3: w = (uint32_t)(al >> 32); break;
+		case 4: w = (uint32_t)clen; break;
+		default: w = 0; break;                   // the reference leaves these 4 pad bytes unspecified
+		}
+		reinterpret_cast<uint32_t *>(rec)[lane] = w;
+	}
+	if (payload_ro) warp_copy_ro(rec + 24, payload, plen, lane);
+	else warp_copy_rw(rec + 24, payload, plen, lane);
+	__syncwarp();
+	if (lane == 0) {
+		s.addr_u = au; s.addr_l = al;
+		s.ts = job.ts ? job.ts[i] : 0;
+		if (job.table.fp) { job.table.fp[2 * (size_t)idx] = fp_hi; job.table.fp[2 * (size_t)idx + 1] = fp_lo; }
+		if (s.vlen == 0) atomicAdd(job.table.entries, 1ull);
+		s.vlen = (uint32_t)clen + 1u;
+	}
+}
+
+template <bool WIDE>
+__global__ void __launch_bounds__(512, 1) k_encode(EncodeJob job) {
+	extern __shared__ __align__(16) uint8_t smem[];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	uint8_t *tab = smem + (size_t)warp * LZ4_TABLE_BYTES;
+	for (;;) {
+		uint32_t i = 0;
+		if (lane == 0) i = atomicAdd(job.work, 1u);
+		i = __shfl_sync(CMB_FULL, i, 0);
+		if (i >= job.n) break;
+		const bool store = job.slot_idx != nullptr;
+		uint32_t idx = 0;
+		if (store) {
+			idx = job.slot_idx[i];
+			// invalid address, or a later chunk of this batch rewrites the same key
+			bool live = idx != 0xffffffffu && job.table.slots[idx].seq == job.seq0 + i;
+			if (!live) { if (lane == 0) job.lens[i] = -1; continue; }
+		}
+		const uint8_t *src = job.pages + (size_t)i * job.page_stride;
+		uint64_t fp_hi = 0, fp_lo = 0;
+		if (job.fps) {
+			warp_fingerprint128(src, job.nbytes, lane, fp_hi, fp_lo);
+			if (lane == 0) { job.fps[2 * (size_t)i] = fp_hi; job.fps[2 * (size_t)i + 1] = fp_lo; }
+		}
+		if (job.accel == 0) {           // comp_accel == 0: raw page, compressed_length 0 (filemap.c:129-133)
+			if (lane == 0) job.lens[i] = 0;
+			if (store) commit_record(job, i, idx, src, job.nbytes, 0, true, fp_hi, fp_lo, lane);
+			continue;
+		}
+		uint8_t *dst = job.stage + (size_t)i * job.stage_stride;
+		uint32_t clen = lz4_encode_warp<WIDE>(src, job.nbytes, dst, job.accel, tab, lane);
+		if (lane == 0) job.lens[i] = (int32_t)clen;
+		if (store) {
+			__syncwarp();
+			commit_record(job, i, idx, dst, clen, (int32_t)clen, false, fp_hi, fp_lo, lane);
+		}
+	}
+}
+
+static int g_sm_count = 0;
+int sm_count() {
+	if (!g_sm_count) {
+		int dev = 0;
+		cudaGetDevice(&dev);
+		cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+		if (g_sm_count <= 0) g_sm_count = 148;
+	}
+	return g_sm_count;
+}
+
+static int env_int(const char *name, int dflt, int lo, int hi) {
+	const char *v = getenv(name);
+	if (!v || !*v) return dflt;
+	int x = atoi(v);
+	return x < lo ? lo : x > hi ? hi : x;
+}
+
+int launch_encode(const EncodeJob &job, cudaStream_t st) {
+	if (job.n == 0) return 0;
+	// Residency is bounded by the 16 KiB position table per chunk: warps/CTA x CTAs/SM x 16 KiB
+	// must fit the 227 KiB of shared memory; what is left of the 228 KiB array serves as L1 for
+	// the page reads.
+	static int warps = env_int("CMB200_ENC_WARPS", 6, 1, 14);
+	static int ctas = env_int("CMB200_ENC_CTAS_PER_SM", 2, 1, 8);
+	size_t smem = (size_t)warps * LZ4_TABLE_BYTES;
+	auto kern = job.nbytes >= LZ4_NARROW_LIMIT ? k_encode<true> : k_encode<false>;
+	CMB_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	CMB_CHECK(cudaMemsetAsync(job.work, 0, sizeof(unsigned int), st));
+	uint32_t grid = (uint32_t)(sm_count() * ctas);
+	uint32_t need = (job.n + warps - 1) / warps;
+	if (grid > need) grid = need;
+	kern<<<grid, warps * 32, smem, st>>>(job);
+	CMB_CHECK(cudaGetLastError());
+	return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// decode
+// ------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256) k_decode(DecodeJob job) {
+	const int lane = threadIdx.x & 31;
+	const uint32_t i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	if (i >= job.n) return;
+	uint8_t *out = job.pages + (size_t)i * job.nbytes;
+	if (job.rec_off) {                                  // store mode
+		if (job.status[i] != ST_HIT) return;
+		const uint8_t *rec = job.arena + job.rec_off[i];
+		uint32_t clen = job.vlen[i] - 1u;
+		if (clen == 0) {                            // raw page (filemap.c:249-251)
+			warp_copy_ro(out, rec + 24, job.nbytes, lane);
+			return;
+		}
+		int used = lz4_decode_warp(rec + 24, clen, out, job.nbytes, lane);
+		if (used != (int)clen && lane == 0) job.status[i] = ST_BAD_DECODE;   // filemap.c:244-248
+	} else {
+		int used = lz4_decode_warp(job.blocks + (size_t)i * job.block_stride, (uint32_t)job.lens[i], out,
+		    job.nbytes, lane);
+		if (lane == 0) job.status[i] = used;
+	}
+}
+
+int launch_decode(const DecodeJob &job, cudaStream_t st) {
+	if (job.n == 0) return 0;
+	const int warps = 8;
+	k_decode<<<(job.n + warps - 1) / warps, warps * 32, 0, st>>>(job);
+	CMB_CHECK(cudaGetLastError());
+	return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// fingerprint alone, stream generator, small launchers
+// ------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256) k_fingerprint(const uint8_t *pages, uint64_t stride, uint32_t nbytes,
+    uint32_t n, uint64_t *fps) {
+	const int lane = threadIdx.x & 31;
+	const uint32_t i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	if (i >= n) return;
+	uint64_t hi, lo;
+	warp_fingerprint128(pages + (size_t)i * stride, nbytes, lane, hi, lo);
+	if (lane == 0) { fps[2 * (size_t)i] = hi; fps[2 * (size_t)i + 1] = lo; }
+}
+
+int launch_fingerprint(const uint8_t *pages, uint64_t stride, uint32_t nbytes, uint32_t n, uint64_t *fps,
+    cudaStream_t st) {
+	if (n == 0) return 0;
+	const int warps = 8;
+	k_fingerprint<<<(n + warps - 1) / warps, warps * 32, 0, st>>>(pages, stride, nbytes, n, fps);
+	CMB_CHECK(cudaGetLastError());
+	return 0;
+}
+
+__global__ void k_streamgen(const uint64_t *cids, uint32_t n, uint64_t seed, uint32_t bsize, uint8_t *out) {
+	const uint32_t words = bsize / 8;
+	const uint64_t total = (uint64_t)n * words;
+	for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+	     g += (uint64_t)gridDim.x * blockDim.x) {
+		uint32_t c = (uint32_t)(g / words), w = (uint32_t)(g % words);
+		reinterpret_cast<uint64_t *>(out)[g] = sg_chunk_word(seed, cids[c], bsize, w);
+	}
+}
+
+int launch_streamgen(const uint64_t *cids, uint32_t n, uint64_t seed, uint32_t bsize, uint8_t *out,
+    cudaStream_t st) {
+	if (n == 0) return 0;
+	k_streamgen<<<sm_count() * 8, 256, 0, st>>>(cids, n, seed, bsize, out);
+	CMB_CHECK(cudaGetLastError());
+	return 0;
+}
+
+#define GRID1D(n) (((n) + 255u) / 256u), 256
+
+int launch_compose(const uint64_t *offset, const uint64_t *nhid, const uint32_t *genid, int pshift,
+    uint32_t n, unsigned long long *addr, uint8_t *valid, unsigned long long *key, cudaStream_t st) {
+	if (n == 0) return 0;
+	k_compose<<<GRID1D(n), 0, st>>>(offset, nhid, genid, pshift, n, addr, valid, key);
+	CMB_CHECK(cudaGetLastError());
+	return 0;
+}
+int launch_upsert(TableView t, const unsigned long long *addr, const uint8_t *valid, uint32_t n,
+    unsigned long long seq0, uint32_t *slot_idx, cudaStream_t st) {
+	if (n == 0) return 0;
+	k_upsert<<<GRID1D(n), 0, st>>>(t, addr, valid, n, seq0, slot_idx);
+	CMB_CHECK(cudaGetLastError());
+	return 0;
+}
+int launch_lookup(TableView t, const unsigned long long *addr, const uint8_t *valid, uint32_t n,
+    int32_t *status, uint64_t *rec_off, uint32_t *vlen, unsigned long long *ts_out, cudaStream_t st) {
+	if (n == 0) return 0;
+	k_lookup<<<GRID1D(n), 0, st>>>(t, addr, valid, n, status, rec_off, vlen, ts_out);
+	CMB_CHECK(cudaGetLastError());
+	return 0;
+}
+int launch_unset(TableView t, ArenaView a, const unsigned long long *addr, uint32_t n, cudaStream_t st) {
+	if (n == 0) return 0;
+	k_unset<<<GRID1D(n), 0, st>>>(t, a, addr, n);
+	CMB_CHECK(cudaGetLastError());
+	return 0;
+}
+__global__ void k_read_fp(TableView t, const unsigned long long *addr, uint32_t n, uint64_t *fp_out, int32_t *ok) {
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	unsigned long long u = addr[2 * i], l = addr[2 * i + 1];
+	uint32_t idx = table_find(t, fnv_addr(u, l));
+	int32_t found = 0;
+	if (idx != 0xffffffffu && t.slots[idx].vlen != 0 && t.slots[idx].addr_u == u && t.slots[idx].addr_l == l) {
+		fp_out[2 * i] = t.fp[2 * (size_t)idx]; fp_out[2 * i + 1] = t.fp[2 * (size_t)idx + 1];
+		found = 1;
+	}
+	ok[i] = found;
+}
+int launch_read_fp(TableView t, const unsigned long long *addr, uint32_t n, uint64_t *fp_out, int32_t *ok,
+    cudaStream_t st) {
+	if (n == 0) return 0;
+	k_read_fp<<<GRID1D(n), 0, st>>>(t, addr, n, fp_out, ok);
+	CMB_CHECK(cudaGetLastError());
+	return 0;
+}
+int launch_sample(TableView t, const unsigned long long *r, uint32_t n, unsigned long long *addr_out,
+    unsigned long long *ts_out, int32_t *ok, cudaStream_t st) {
+	if (n == 0) return 0;
+	k_sample<<<GRID1D(n), 0, st>>>(t, r, n, addr_out, ts_out, ok);
+	CMB_CHECK(cudaGetLastError());
+	return 0;
+}
+
+}  // namespace cmb

@@ -1,0 +1,116 @@
+// kernels.h — launch interface between the engine (host C++) and the sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cmb {
+
+// One record of the HBM key table (64 bytes).  Replaces the reference's LMDB B+tree entry:
+// key = FNV-1a-64 of the 16 address bytes (cachemap/filemap.c:18-24), one record per key
+// (mdb_put_attr overwrite, filemap.c:143), attr = put timestamp (filemap.c:143, cachemap.c:195).
+struct Slot {
+	unsigned long long key;      // 0 = never used, ~0 = deleted; those two key values live in side slots
+	unsigned long long addr_u;   // stored address, verified on get (filemap.c:236-240)
+	unsigned long long addr_l;
+	unsigned long long rec_off;  // arena offset of {24-byte data_prefix, payload} (filemap.c:140-147)
+	uint32_t vlen;               // 0 = no valid record, else compressed_length + 1 (0+1 = raw page)
+	uint32_t alloc;              // arena bytes reserved at rec_off
+	unsigned long long ts;       // LMDB node attribute of the reference
+	unsigned long long seq;      // stream order of the last put that claimed this key
+	unsigned long long spare;
+};
+static_assert(sizeof(Slot) == 64, "slot layout");
+
+constexpr unsigned long long KEY_EMPTY = 0ull;
+constexpr unsigned long long KEY_TOMB = ~0ull;
+
+struct TableView {
+	Slot *slots;                 // cap + 2 entries; [cap] holds key 0, [cap+1] holds key ~0
+	uint64_t cap;                // power of two
+	unsigned long long *entries; // live records
+	unsigned long long *tombs;   // deleted main-table slots (rebuild trigger)
+	uint64_t *fp;                // optional, 2 x u64 per slot {hi, lo}
+};
+
+struct ArenaView {
+	uint8_t *base;
+	uint64_t size;
+	unsigned long long *head;     // bump pointer
+	unsigned long long *garbage;  // bytes orphaned by relocated / deleted records
+	unsigned long long *dropped;  // puts dropped because the arena was full (filemap.c:154-157 analogue)
+};
+
+enum LookupStatus : int32_t {
+	ST_MISS = 0,
+	ST_HIT = 1,
+	ST_INVALID = 2,      // page number overflowed 44 bits: not counted as a request (cachemap.c:173-174)
+	ST_BAD_ENTRY = 3,    // key present with another address (filemap.c:236-240)
+	ST_BAD_DECODE = 4,   // decoder consumed != stored length (filemap.c:244-248)
+};
+
+struct EncodeJob {
+	const uint8_t *pages;    // n chunks, `page_stride` apart, 16-byte aligned
+	uint64_t page_stride;
+	uint32_t nbytes;         // chunk length
+	uint32_t n;
+	uint32_t accel;          // 0 = store raw (cachemap.h comp_accel==0)
+	uint8_t *stage;          // n x stage_stride scratch for blocks
+	uint64_t stage_stride;
+	int32_t *lens;           // out: block length, -1 = chunk skipped (superseded inside the batch)
+	uint64_t *fps;           // out, optional: 2 x u64 per chunk {hi, lo}
+	unsigned int *work;      // dynamic work counter (zeroed by the launcher)
+	// store mode (all null/0 for codec-only use)
+	const uint32_t *slot_idx; // per chunk, from the upsert kernel; 0xffffffff = invalid address
+	const unsigned long long *addr; // per chunk {u,l}
+	const unsigned long long *ts;   // per chunk
+	unsigned long long seq0;  // sequence of chunk 0
+	TableView table;
+	ArenaView arena;
+};
+
+int launch_encode(const EncodeJob &job, cudaStream_t st);
+
+struct DecodeJob {
+	uint32_t n;
+	uint32_t nbytes;
+	uint8_t *pages;              // n x nbytes out
+	int32_t *status;             // in/out (store mode) or out consumed (codec mode)
+	// codec mode
+	const uint8_t *blocks;       // n blocks, block_stride apart
+	uint64_t block_stride;
+	const int32_t *lens;
+	// store mode
+	const uint64_t *rec_off;     // per request, from lookup
+	const uint32_t *vlen;
+	const uint8_t *arena;
+};
+int launch_decode(const DecodeJob &job, cudaStream_t st);
+
+int launch_fingerprint(const uint8_t *pages, uint64_t stride, uint32_t nbytes, uint32_t n,
+    uint64_t *fps, cudaStream_t st);
+
+// addr[2i],addr[2i+1] = {u,l}; valid[i] = 0 marks a rejected address (cachemap.c:160-161).
+int launch_compose(const uint64_t *offset, const uint64_t *nhid, const uint32_t *genid, int pshift,
+    uint32_t n, unsigned long long *addr, uint8_t *valid, unsigned long long *key, cudaStream_t st);
+
+int launch_upsert(TableView t, const unsigned long long *addr, const uint8_t *valid, uint32_t n,
+    unsigned long long seq0, uint32_t *slot_idx, cudaStream_t st);
+
+int launch_lookup(TableView t, const unsigned long long *addr, const uint8_t *valid, uint32_t n,
+    int32_t *status, uint64_t *rec_off, uint32_t *vlen, unsigned long long *ts_out, cudaStream_t st);
+
+int launch_unset(TableView t, ArenaView a, const unsigned long long *addr, uint32_t n, cudaStream_t st);
+
+// Policy-equivalent of filemap_get_rand (filemap.c:264-314): first live slot at or after r.
+int launch_sample(TableView t, const unsigned long long *r, uint32_t n, unsigned long long *addr_out,
+    unsigned long long *ts_out, int32_t *ok, cudaStream_t st);
+
+int launch_read_fp(TableView t, const unsigned long long *addr, uint32_t n, uint64_t *fp_out, int32_t *ok,
+    cudaStream_t st);
+
+int launch_streamgen(const uint64_t *cids, uint32_t n, uint64_t seed, uint32_t bsize, uint8_t *out,
+    cudaStream_t st);
+
+int sm_count();
+
+}  // namespace cmb

@@ -1,0 +1,139 @@
+/*
+ * cachemap_b200.h — C ABI of the B200 cachemap engine (batch extension + kernel-level entries).
+ *
+ * The drop-in surface is include/cachemap.h + include/filemap.h (same prototypes as the
+ * reference's cachemap/cachemap.h:33-47 and cachemap/filemap.h:19-29).  This header is the layer
+ * under it: batched put/get over many chunks per call (the reference's API moves one page per
+ * call — edgefs.c:1165,1191,1224 — which cannot feed a GPU), plus direct entry
+ * points to the individual kernels so that parity tests can compare each one with the oracle.
+ *
+ * Plain C: pointers and sizes only, no CUDA or torch types.  "host" pointers may be pageable or
+ * page-locked (cmb200_host_alloc gives page-locked memory; transfers from it run at full PCIe
+ * rate).  "dev" pointers are device addresses in the engine's CUDA device.
+ * All functions return 0 on success and -1 on failure unless stated; cmb200_last_error() then
+ * describes the failure.  There is no CPU fallback anywhere: without a usable CUDA device every
+ * entry point fails.
+ */
+#ifndef CACHEMAP_B200_H
+#define CACHEMAP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cmb200_engine cmb200_engine;
+
+/* 16-byte page address, {u = nhid_small, l = page | genid << 44} (cachemap/uint128.h:4,
+ * cachemap/cachemap.c:151-166). */
+typedef struct { uint64_t u; uint64_t l; } cmb200_addr;
+
+#define CMB200_FINGERPRINT 1u   /* compute + keep the EF128 content fingerprint of every put */
+
+typedef struct cmb200_config {
+	int device;             /* CUDA ordinal, -1 = current device */
+	int pshift;             /* page shift: chunk = 1 << pshift bytes (edgefs -p, edgefs.c:2043-2048) */
+	int accel;              /* LZ4 acceleration, 0 = store raw (cachemap_create comp_accel) */
+	uint64_t capacity;      /* entries before eviction starts (cachemap_create capacity) */
+	uint64_t arena_bytes;   /* HBM arena for records, 0 = sized from capacity and free memory */
+	uint64_t table_slots;   /* key-table slots (power of two), 0 = 2 x capacity rounded up */
+	uint32_t max_batch;     /* chunks per device batch, 0 = 4096 */
+	uint32_t flags;
+} cmb200_config;
+
+/* per-request result of a get */
+enum {
+	CMB200_MISS = 0,
+	CMB200_HIT = 1,
+	CMB200_INVALID = 2,     /* address rejected: not counted as a request (cachemap.c:173-174) */
+	CMB200_BAD_ENTRY = 3,   /* key present under another address: a miss (filemap.c:236-240) */
+	CMB200_BAD_DECODE = 4   /* decoded length != stored length: a miss (filemap.c:244-248) */
+};
+
+const char *cmb200_last_error(void);
+int cmb200_device_count(void);
+
+cmb200_engine *cmb200_engine_create(const cmb200_config *cfg);
+void cmb200_engine_destroy(cmb200_engine *e);
+
+void *cmb200_host_alloc(size_t bytes);        /* page-locked host memory */
+void cmb200_host_free(void *p);
+void *cmb200_dev_alloc(cmb200_engine *e, size_t bytes);
+void cmb200_dev_free(cmb200_engine *e, void *p);
+int cmb200_memcpy_h2d(cmb200_engine *e, void *dev, const void *host, size_t bytes);
+int cmb200_memcpy_d2h(cmb200_engine *e, void *host, const void *dev, size_t bytes);
+void *cmb200_stream(cmb200_engine *e);        /* the engine's compute cudaStream_t, for event timing */
+int cmb200_sync(cmb200_engine *e);
+
+/* filemap_set for n chunks (cachemap/filemap.c:112-158): pages = n x (1<<pshift) bytes.
+ * valid (nullable) = per-chunk flag, 0 skips the chunk (rejected address).  ts (nullable) = the
+ * LMDB attribute.  Chunks are applied in array order: a later chunk with the same key wins.
+ * lens_out (nullable, host) receives each stored compressed_length, or -1 for skipped chunks. */
+int cmb200_put_batch(cmb200_engine *e, size_t n, const cmb200_addr *addr, const uint8_t *valid,
+    const void *pages_host, const uint64_t *ts, int32_t *lens_out);
+int cmb200_put_batch_dev(cmb200_engine *e, size_t n, const cmb200_addr *addr, const uint8_t *valid,
+    const void *pages_dev, const uint64_t *ts, int32_t *lens_out);
+
+/* filemap_get for n requests (cachemap/filemap.c:217-262).  status_out[i] is one of CMB200_*;
+ * pages_out receives 1<<pshift bytes per request (untouched for non-hits). */
+int cmb200_get_batch(cmb200_engine *e, size_t n, const cmb200_addr *addr, const uint8_t *valid,
+    void *pages_out_host, int32_t *status_out);
+int cmb200_get_batch_dev(cmb200_engine *e, size_t n, const cmb200_addr *addr, const uint8_t *valid,
+    void *pages_out_dev, int32_t *status_out);
+
+/* filemap_unset (filemap.c:188-215), filemap_entries (filemap.c:316-330),
+ * filemap_get_rand (filemap.c:264-314; policy-equivalent: first live record at or after r). */
+int cmb200_unset_batch(cmb200_engine *e, size_t n, const cmb200_addr *addr);
+uint64_t cmb200_entries(cmb200_engine *e);
+int cmb200_sample(cmb200_engine *e, size_t n, const uint64_t *r, cmb200_addr *addr_out,
+    uint64_t *ts_out, int32_t *ok_out);
+
+/* Copies the stored record of each address — the bytes the reference keeps in LMDB:
+ * 24-byte data_prefix + payload (filemap.c:9-12,140-147) — into out (stride bytes apart) and its
+ * total length into len_out (-1 = absent). */
+int cmb200_read_records(cmb200_engine *e, size_t n, const cmb200_addr *addr, void *out_host,
+    size_t stride, int32_t *len_out);
+/* EF128 of the stored records (engine created with CMB200_FINGERPRINT): fp_out[2i]=hi, [2i+1]=lo. */
+int cmb200_read_fingerprints(cmb200_engine *e, size_t n, const cmb200_addr *addr, uint64_t *fp_out,
+    int32_t *ok_out);
+
+typedef struct cmb200_stats {
+	uint64_t entries, table_slots, tombstones;
+	uint64_t arena_bytes, arena_used, arena_garbage, dropped_puts;
+	uint64_t put_chunks, get_requests, get_hits, kernel_launches;
+} cmb200_stats;
+int cmb200_get_stats(cmb200_engine *e, cmb200_stats *out);
+
+/* ---- kernel-level entry points (parity tests, benchmarks); device = CUDA ordinal or -1 ---- */
+
+/* cachemap.c:151-166 + filemap.c:18-24 on the device. */
+int cmb200_compose_keys(int device, size_t n, const uint64_t *offset, const uint64_t *nhid,
+    const uint32_t *genid, int pshift, cmb200_addr *addr_out, uint8_t *valid_out, uint64_t *key_out);
+
+/* LZ4_compress_fast(page, dst, nbytes, nbytes+1024, accel) for n pages `stride` bytes apart
+ * (stride multiple of 16); blocks_out rows are out_stride apart (>= nbytes + nbytes/255 + 16).
+ * fp_out nullable: EF128 {hi,lo} per page from the same (fused) kernel. */
+int cmb200_lz4_encode_batch(int device, const void *pages_host, size_t n, uint32_t nbytes,
+    size_t stride, int accel, void *blocks_out_host, size_t out_stride, int32_t *lens_out,
+    uint64_t *fp_out);
+/* LZ4_decompress_fast(block, page, nbytes): consumed_out[i] = bytes consumed or < 0. */
+int cmb200_lz4_decode_batch(int device, const void *blocks_host, size_t in_stride, const int32_t *lens,
+    size_t n, uint32_t nbytes, void *pages_out_host, int32_t *consumed_out);
+int cmb200_fingerprint_batch(int device, const void *pages_host, size_t n, uint32_t nbytes,
+    size_t stride, uint64_t *fp_out);
+
+/* ---- synthetic streams, same definition on host and device ---- */
+void cmb200_gen_chunk_host(uint64_t seed, uint64_t cid, uint32_t bsize, void *out);
+int cmb200_gen_chunks_dev(cmb200_engine *e, uint64_t seed, const uint64_t *cids_host, size_t n,
+    void *out_dev);
+/* cid[k] for a stream of n chunks with duplicate fraction dup (same-address repeats);
+ * returns the number of distinct chunks. */
+uint64_t cmb200_gen_stream_ids(uint64_t seed2, size_t n, double dup, uint64_t first_cid, uint64_t *cid_out);
+void cmb200_gen_addr(uint64_t seed, uint64_t cid, int pshift, uint64_t *offset_out, uint64_t *nhid_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,222 @@
+"""GPU parity, store level: hit/miss decisions, stored records and counters of the CUDA cachemap
+against the reference trace fixture and the oracle's store model, through the drop-in C API."""
+import hashlib
+import json
+import os
+import threading
+
+import numpy as np
+import pytest
+
+import datagen
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def sha(b):
+    return hashlib.sha256(bytes(b)).hexdigest()
+
+
+@pytest.fixture(autouse=True)
+def small_engine(monkeypatch):
+    monkeypatch.setenv("CMB200_ARENA_MB", "512")
+    monkeypatch.setenv("CMB200_MAX_BATCH", "512")
+    monkeypatch.setenv("CMB200_FINGERPRINT", "1")
+
+
+def test_reference_trace_through_cachemap_api(E, gpu, tmp_path):
+    """config 0 of BASELINE.json: 16 x 64 KiB + the edge cases, one call per page, same calls the
+    reference answered when tools/gen_golden.py recorded the fixture."""
+    t = json.load(open(os.path.join(GOLD, "store_trace.json")))
+    assert not E.Cachemap(str(tmp_path), 1023, t["accel"], t["pshift"]).ok
+    assert not E.Cachemap(str(tmp_path / "nope"), 1024, t["accel"], t["pshift"]).ok
+    cm = E.Cachemap(str(tmp_path), t["capacity"], t["accel"], t["pshift"])
+    assert cm.ok
+    gets = []
+    for kind, off, nh, gen, content in t["ops"]:
+        if kind == "put":
+            cm.put(off, nh, gen, datagen.make_page(content[0], cm.bsize, content[1]))
+            gets.append(None)
+        else:
+            p = cm.get(off, nh, gen)
+            gets.append("miss" if p is None else sha(p))
+    assert gets == t["gets"]
+    assert cm.counters() == (t["requests"], t["hits"])
+    assert E.lib().filemap_entries(_pages_ptr(cm)) == t["entries"]
+    cm.free()
+
+
+def _pages_ptr(cm):
+    import ctypes
+    return ctypes.cast(cm.h, ctypes.POINTER(ctypes.c_void_p))[0]       # struct cachemap { pages, ...
+
+
+def test_records_are_the_references_bytes(E, gpu, oracle):
+    """What sits in the arena for an address is byte for byte the LMDB value of the reference:
+    24-byte data_prefix + LZ4 block (filemap.c:140-147)."""
+    eng = E.Engine(pshift=16, accel=12, capacity=4096, arena_bytes=256 << 20, max_batch=256,
+                   flags=E.FINGERPRINT)
+    model = oracle.StoreModel(16, 12)
+    n = 300
+    cids, _ = E.gen_stream_ids(n, 0.4)
+    off, nh = E.gen_addr(42, cids, 16)
+    pages = np.stack([E.gen_chunk_host(42, int(c), 65536) for c in cids])
+    u, l = nh, off >> np.uint64(16)
+    lens = eng.put(u, l, pages, ts=np.arange(n, dtype=np.uint64))
+    for i in range(n):
+        model.put(int(off[i]), int(nh[i]), 0, pages[i])
+    assert eng.entries() == model.entries()
+    recs = eng.read_records(u, l)
+    for i in range(n):
+        assert recs[i] == model.record_bytes(int(u[i]), int(l[i])), i
+    # lens: -1 for chunks superseded inside the batch, else the stored compressed_length
+    last = {}
+    for i in range(n):
+        last[(int(u[i]), int(l[i]))] = i
+    for i in range(n):
+        if last[(int(u[i]), int(l[i]))] == i:
+            assert lens[i] == len(recs[i]) - 24
+        else:
+            assert lens[i] == -1
+    fps, ok = eng.read_fingerprints(u, l)
+    assert ok.all()
+    for i in range(0, n, 17):
+        assert (int(fps[i, 0]), int(fps[i, 1])) == oracle.fingerprint128(pages[last[(int(u[i]), int(l[i]))]])
+    out, status = eng.get(u, l)
+    assert (status == E.HIT).all() and all((out[i] == pages[last[(int(u[i]), int(l[i]))]]).all() for i in range(n))
+    eng.close()
+
+
+def test_store_semantics_vs_model(E, gpu, oracle):
+    """Random put / get / unset batches against the store model: hit/miss, bad-entry, overwrite,
+    entry count; 4 KiB pages so the oracle finishes in seconds."""
+    pshift, bs = 12, 4096
+    eng = E.Engine(pshift=pshift, accel=12, capacity=8192, arena_bytes=64 << 20, max_batch=128)
+    model = oracle.StoreModel(pshift, 12)
+    w = datagen.words(77, 4000)
+    universe = [(int(w[i] % np.uint64(5)) + 1, int(w[i + 1] % np.uint64(300))) for i in range(0, 600, 2)]
+    step = 0
+    for rnd in range(12):
+        k = 40 + rnd * 13
+        pick = [universe[int(x % np.uint64(len(universe)))] for x in datagen.words(1000 + rnd, k)]
+        u = np.array([p[0] for p in pick], dtype=np.uint64)
+        l = np.array([p[1] for p in pick], dtype=np.uint64)
+        if rnd % 3 != 2:
+            pages = np.stack([datagen.make_page("RTZMPA"[(step + i) % 6], bs, step + i) for i in range(k)])
+            eng.put(u, l, pages)
+            for i in range(k):
+                model.put(int(l[i]) << pshift, int(u[i]), 0, pages[i])
+            step += k
+        else:
+            eng.unset(u[: k // 3], l[: k // 3])
+            for i in range(k // 3):
+                model.unset(int(u[i]), int(l[i]))
+        assert eng.entries() == model.entries()
+        q = [universe[int(x % np.uint64(len(universe)))] for x in datagen.words(2000 + rnd, 150)]
+        qu = np.array([p[0] for p in q], dtype=np.uint64)
+        ql = np.array([p[1] for p in q], dtype=np.uint64)
+        out, status = eng.get(qu, ql)
+        for i in range(len(q)):
+            exp = model.get(int(ql[i]) << pshift, int(qu[i]), 0)
+            assert (status[i] == E.HIT) == (exp is not None), (rnd, i)
+            if exp is not None:
+                assert out[i].tobytes() == exp
+    st = eng.stats()
+    assert st["dropped_puts"] == 0 and st["entries"] == model.entries()
+    eng.close()
+
+
+def test_raw_mode_and_other_page_sizes(E, gpu, oracle, tmp_path):
+    for pshift, accel in ((12, 0), (13, 12), (15, 12), (17, 12), (16, 0)):
+        cm = E.Cachemap(str(tmp_path), 2048, accel, pshift)
+        bs = 1 << pshift
+        n = 40
+        pages = np.stack([datagen.make_page("RTZM"[i % 4], bs, 5 * pshift + i) for i in range(n)])
+        off = (np.arange(n, dtype=np.uint64) * np.uint64(3)) << np.uint64(pshift)
+        nh = np.full(n, 0xABCDEF, dtype=np.uint64)
+        gen = np.zeros(n, dtype=np.uint32)
+        cm.put_batch(off, nh, gen, pages)
+        out, hit = cm.get_batch(off, nh, gen)
+        assert hit.all() and (out == pages).all(), (pshift, accel)
+        _, miss = cm.get_batch(off + np.uint64(bs), nh, gen)
+        assert not miss.any()
+        eng = E.Engine.__new__(E.Engine); eng.h = cm.engine_handle(); eng.bsize = bs
+        recs = eng.read_records(nh, off >> np.uint64(pshift))
+        model = oracle.StoreModel(pshift, accel)
+        for i in range(n):
+            model.put(int(off[i]), int(nh[i]), 0, pages[i])
+            assert recs[i] == model.record_bytes(int(nh[i]), int(off[i]) >> pshift), (pshift, accel, i)
+        eng.h = None
+        assert cm.counters() == (2 * n, n)
+        cm.free()
+
+
+def test_concurrent_callers_are_combined(E, gpu, tmp_path):
+    """libfuse runs edgefs_read/write on many threads (edgefs.c:78,2194): concurrent single-page
+    calls must be safe and see their own writes."""
+    cm = E.Cachemap(str(tmp_path), 4096, 12, 16)
+    errs = []
+
+    def worker(t):
+        try:
+            for i in range(12):
+                page = datagen.make_page("RTZM"[(t + i) % 4], 65536, 100 * t + i)
+                off = (t * 64 + i) << 16
+                cm.put(off, 0x1000 + t, 0, page)
+                back = cm.get(off, 0x1000 + t, 0)
+                assert back == page.tobytes(), (t, i)
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=worker, args=(t,)) for t in range(8)]
+    [x.start() for x in th]
+    [x.join() for x in th]
+    assert not errs, errs
+    assert cm.counters() == (96, 96)
+    cm.free()
+
+
+def test_async_put_queue(E, gpu, tmp_path):
+    cm = E.Cachemap(str(tmp_path), 4096, 12, 15)          # cachemap_test.c shape: 32 KiB pages
+    pages = [datagen.make_page("TZ"[i % 2], 32768, i) for i in range(200)]
+    for i, p in enumerate(pages):
+        cm.put(i * 4096 * 8, 5 * i + 1, i, p, async_=True)
+    cm_h = cm.h
+    cm.free()                                             # drains the queue (cachemap.c:218-232)
+    assert cm_h
+    cm = E.Cachemap(str(tmp_path), 4096, 12, 15)
+    for i, p in enumerate(pages[:50]):
+        cm.put(i * 4096 * 8, 5 * i + 1, i, p, async_=True)
+    import time
+    deadline = time.time() + 20
+    got = 0
+    while time.time() < deadline:
+        got = sum(cm.get(i * 4096 * 8, 5 * i + 1, i) == pages[i].tobytes() for i in range(50))
+        if got == 50:
+            break
+        time.sleep(0.05)
+    assert got == 50
+    cm.free()
+
+
+def test_eviction_keeps_capacity(E, gpu, tmp_path):
+    """Policy equivalence only: entries never exceed capacity, recent puts
+    survive more often than old ones."""
+    cm = E.Cachemap(str(tmp_path), 1024, 12, 12)
+    bs = 4096
+    total = 3000
+    pages = np.stack([datagen.make_page("T", bs, i) for i in range(total)])
+    nh = np.full(total, 9, dtype=np.uint64)
+    gen = np.zeros(total, dtype=np.uint32)
+    off = np.arange(total, dtype=np.uint64) << np.uint64(12)
+    for at in range(0, total, 100):
+        cm.put_batch(off[at:at + 100], nh[at:at + 100], gen[at:at + 100], pages[at:at + 100])
+        import time
+        time.sleep(0.005)                                 # CLOCK_REALTIME_COARSE granularity
+    entries = E.lib().filemap_entries(_pages_ptr(cm))
+    assert entries <= 1024
+    _, hit = cm.get_batch(off, nh, gen)
+    assert hit.sum() == entries
+    assert hit[-500:].mean() > hit[:500].mean()
+    cm.free()

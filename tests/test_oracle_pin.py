@@ -1,0 +1,125 @@
+"""Pins the CPU oracle (oracle/) to the reference: against the committed golden vectors that
+tools/gen_golden.py produced with the compiled reference, and — when oracle/_ref is present —
+against the compiled reference live.  CPU only."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import datagen
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def sha(b):
+    return hashlib.sha256(bytes(b)).hexdigest()
+
+
+def load(name):
+    with open(os.path.join(GOLD, name)) as f:
+        return json.load(f)
+
+
+def test_fnv_and_key_kats(oracle):
+    k = load("keys.json")
+    assert k["sizeof_uint128"] == 16
+    for s, h in k["strings"]:
+        assert oracle.fnv1a64(s.encode()) == int(h, 16)
+    for u, l, h in k["addrs"]:
+        assert oracle.addr_key(int(u, 16), int(l, 16)) == int(h, 16)
+    # SURVEY.md §8c known answers
+    assert oracle.fnv1a64(b"") == 0xcbf29ce484222325
+    assert oracle.addr_key(0x1122334455667788, (7 << 44) | 3) == 0x1e041ed74a444846
+    assert oracle.addr_key(0x1122334455667788, (7 << 44) | 3) & 31 == 6
+
+
+def test_addr_compose(oracle):
+    assert oracle.addr_compose(65537, 9, 0, 16) == (9, 1)            # offset truncated, no alignment check
+    assert oracle.addr_compose(3 << 16, 9, 7, 16) == (9, (7 << 44) | 3)
+    assert oracle.addr_compose((1 << 44) << 16, 9, 0, 16) is None    # cachemap.c:160-161
+    assert oracle.addr_compose(((1 << 44) - 1) << 12, 9, 0, 12) == (9, (1 << 44) - 1)
+    assert oracle.addr_compose(0, 9, (1 << 20) + 7, 16) == (9, 7 << 44)   # genid keeps 20 bits
+    assert oracle.record_prefix(1, 2, 267) == (1).to_bytes(8, "little") + (2).to_bytes(8, "little") + \
+        (267).to_bytes(4, "little") + b"\0" * 4
+
+
+def test_lz4_golden_vectors(oracle):
+    g = load("lz4_blocks.json")
+    assert len(g["cases"]) == len(datagen.codec_cases())
+    for rec in g["cases"]:
+        page = datagen.make_page(rec["kind"], rec["n"], rec["seed"])
+        assert sha(page) == rec["in_sha256"], rec
+        blk = oracle.lz4_encode(page, rec["accel"])
+        assert len(blk) == rec["len"] and sha(blk) == rec["sha256"], rec
+        if "hex" in rec:
+            assert blk.hex() == rec["hex"]
+        if rec["n"]:
+            back, used = oracle.lz4_decode(blk, rec["n"])
+            assert used == len(blk) and back == page.tobytes(), rec
+
+
+def test_lz4_known_answers(oracle):
+    # incompressible 64 KiB -> 65 794 bytes; zero page -> 267 bytes; bound
+    assert oracle.lib().ef_lz4_bound(65536) == 65809
+    assert len(oracle.lz4_encode(datagen.make_page("R", 65536, 1), 12)) == 65794
+    assert len(oracle.lz4_encode(np.zeros(65536, dtype=np.uint8), 12)) == 267
+
+
+def test_decoder_rejects_malformed(oracle):
+    page = datagen.make_page("T", 4096, 5)
+    blk = oracle.lz4_encode(page, 12)
+    assert oracle.lz4_decode(blk[:-3], 4096)[1] < 0               # truncated
+    assert oracle.lz4_decode(blk, 4095)[1] != len(blk)            # wrong size never "consumes" all
+    assert oracle.lz4_decode(b"\x10\x41\x00\x00", 4096)[1] < 0    # offset 0
+
+
+def test_oracle_vs_reference_live(oracle):
+    if oracle.ref() is None:
+        pytest.skip("oracle/_ref not built (no /root/reference here); golden vectors cover this")
+    assert oracle.ref().LZ4_versionString() == b"1.8.1"
+    n_cases = 0
+    for rep in range(2):
+        for n in (4096, 16384, 65536, 131072, 65546, 65547, 13, 12, 1, 777):
+            for accel in (12, 1, 0, 5, 200):
+                for kind in "RTZMPAX":
+                    page = datagen.make_page(kind, n, 10_000 * rep + n + accel + ord(kind))
+                    a = oracle.lz4_encode(page, accel)
+                    b = oracle.ref_lz4_encode(page, accel)
+                    assert a == b, (kind, n, accel)
+                    back, used = oracle.ref_lz4_decode(a, n)
+                    assert back == page.tobytes() and used == len(a)
+                    n_cases += 1
+    assert n_cases == 700
+
+
+def test_store_model_matches_reference_trace(oracle):
+    t = load("store_trace.json")
+    m = oracle.StoreModel(t["pshift"], t["accel"])
+    gets = []
+    for kind, off, nh, gen, content in t["ops"]:
+        if kind == "put":
+            m.put(off, nh, gen, datagen.make_page(content[0], 1 << t["pshift"], content[1]))
+            gets.append(None)
+        else:
+            p = m.get(off, nh, gen)
+            gets.append("miss" if p is None else sha(p))
+    assert gets == t["gets"]
+    assert (m.entries(), m.requests, m.hits) == (t["entries"], t["requests"], t["hits"])
+
+
+def test_fingerprint_self_consistency(oracle):
+    """EF128 has no reference definition (parity unpinned): frozen KATs of this oracle plus
+    basic sanity (length sensitivity, single-bit sensitivity, padding is not aliasing)."""
+    f = oracle.fingerprint128
+    assert f(b"") == (16344626119028627888, 17509804346615072515)
+    assert f(b"abc") == (8640923672218744830, 2380023549751616974)
+    a = datagen.make_page("R", 65536, 3)
+    b = a.copy(); b[40000] ^= 1
+    assert f(a) != f(b)
+    assert f(a[:65535]) != f(a) and f(np.append(a, np.uint8(0))) != f(a)
+    z1, z2 = np.zeros(512, np.uint8), np.zeros(513, np.uint8)
+    assert f(z1) != f(z2)
+    seen = {f(datagen.make_page("Z", 4096, s)) for s in range(200)}
+    assert len(seen) == len({bytes(datagen.make_page("Z", 4096, s)) for s in range(200)})
