@@ -43,7 +43,8 @@ class Config(C.Structure):
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "entries", "table_slots", "tombstones", "arena_bytes", "arena_used", "arena_garbage",
-        "dropped_puts", "put_chunks", "get_requests", "get_hits", "kernel_launches")]
+        "dropped_puts", "put_chunks", "get_requests", "get_hits", "kernel_launches",
+        "encode_kernel_ns", "encode_kernel_launches", "decode_kernel_ns", "decode_kernel_launches")]
 
 
 def library_path() -> str:

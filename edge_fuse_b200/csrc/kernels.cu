@@ -42,19 +42,43 @@ __device__ __forceinline__ unsigned long long ld_key(const Slot *s) {
 	return *reinterpret_cast<const volatile unsigned long long *>(&s->key);
 }
 
-// Finds the slot holding `key`, claiming a fresh one if absent.  Returns cap-relative index, or
-// 0xffffffff when the table is full.
+// Finds the slot holding `key`, claiming one if absent.  Returns the slot index, or 0xffffffff
+// when the table is full.  A deleted slot (tombstone) met on the way is reused, but only after the
+// whole probe chain has been searched for the key, and by CAS, so that concurrent claimers of the
+// same key inside one kernel converge on one slot: they walk the same chain, so they either agree
+// on the first tombstone, or the loser of a CAS rescans and finds the winner's entry.
 __device__ uint32_t table_find_or_claim(const TableView &t, unsigned long long key) {
 	if (key == KEY_EMPTY) return (uint32_t)t.cap;
 	if (key == KEY_TOMB) return (uint32_t)t.cap + 1;
-	uint64_t i = home_slot(key, t.cap);
-	for (uint64_t n = 0; n < t.cap; n++, i = (i + 1) & (t.cap - 1)) {
-		unsigned long long cur = ld_key(&t.slots[i]);
-		if (cur == key) return (uint32_t)i;
-		if (cur == KEY_EMPTY) {
-			unsigned long long old = atomicCAS(&t.slots[i].key, KEY_EMPTY, key);
-			if (old == KEY_EMPTY || old == key) return (uint32_t)i;
+	for (int attempt = 0; attempt < 64; attempt++) {
+		uint64_t i = home_slot(key, t.cap);
+		uint64_t tomb = ~0ull;
+		bool retry = false;
+		for (uint64_t n = 0; n < t.cap; n++, i = (i + 1) & (t.cap - 1)) {
+			unsigned long long cur = ld_key(&t.slots[i]);
+			if (cur == key) return (uint32_t)i;
+			if (cur == KEY_TOMB) { if (tomb == ~0ull) tomb = i; continue; }
+			if (cur == KEY_EMPTY) {
+				if (tomb != ~0ull) {
+					unsigned long long old = atomicCAS(&t.slots[tomb].key, KEY_TOMB, key);
+					if (old == KEY_TOMB) { atomicAdd(t.tombs, (unsigned long long)-1ll); return (uint32_t)tomb; }
+					if (old == key) return (uint32_t)tomb;
+					retry = true;           // someone else took that tombstone: rescan
+					break;
+				}
+				unsigned long long old = atomicCAS(&t.slots[i].key, KEY_EMPTY, key);
+				if (old == KEY_EMPTY || old == key) return (uint32_t)i;
+				// lost the empty slot to another key: keep walking from here
+			}
 		}
+		if (retry) continue;
+		if (tomb != ~0ull) {        // chain wrapped without an empty slot: still may reuse a tombstone
+			unsigned long long old = atomicCAS(&t.slots[tomb].key, KEY_TOMB, key);
+			if (old == KEY_TOMB) { atomicAdd(t.tombs, (unsigned long long)-1ll); return (uint32_t)tomb; }
+			if (old == key) return (uint32_t)tomb;
+			continue;
+		}
+		break;
 	}
 	return 0xffffffffu;
 }

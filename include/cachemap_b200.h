@@ -38,7 +38,7 @@ typedef struct cmb200_config {
 	int accel;              /* LZ4 acceleration, 0 = store raw (cachemap_create comp_accel) */
 	uint64_t capacity;      /* entries before eviction starts (cachemap_create capacity) */
 	uint64_t arena_bytes;   /* HBM arena for records, 0 = sized from capacity and free memory */
-	uint64_t table_slots;   /* key-table slots (power of two), 0 = 2 x capacity rounded up */
+	uint64_t table_slots;   /* key-table slots (power of two), 0 = 4 x capacity rounded up */
 	uint32_t max_batch;     /* chunks per device batch, 0 = 4096 */
 	uint32_t flags;
 } cmb200_config;
@@ -103,6 +103,8 @@ typedef struct cmb200_stats {
 	uint64_t entries, table_slots, tombstones;
 	uint64_t arena_bytes, arena_used, arena_garbage, dropped_puts;
 	uint64_t put_chunks, get_requests, get_hits, kernel_launches;
+	/* summed CUDA-event durations of the encode / decode kernel launches (last 64 per call) */
+	uint64_t encode_kernel_ns, encode_kernel_launches, decode_kernel_ns, decode_kernel_launches;
 } cmb200_stats;
 int cmb200_get_stats(cmb200_engine *e, cmb200_stats *out);
 

@@ -70,15 +70,17 @@ def test_records_are_the_references_bytes(E, gpu, oracle):
     recs = eng.read_records(u, l)
     for i in range(n):
         assert recs[i] == model.record_bytes(int(u[i]), int(l[i])), i
-    # lens: -1 for chunks superseded inside the batch, else the stored compressed_length
+    # lens: -1 for a chunk superseded by a later one of the same device batch (max_batch=256),
+    # else the compressed_length that was stored when the chunk was applied
     last = {}
     for i in range(n):
         last[(int(u[i]), int(l[i]))] = i
     for i in range(n):
-        if last[(int(u[i]), int(l[i]))] == i:
-            assert lens[i] == len(recs[i]) - 24
-        else:
+        later_same_batch = [j for j in range(i + 1, (i // 256 + 1) * 256) if j < n and (u[j], l[j]) == (u[i], l[i])]
+        if later_same_batch:
             assert lens[i] == -1
+        else:
+            assert lens[i] == len(oracle.lz4_encode(pages[i], 12))
     fps, ok = eng.read_fingerprints(u, l)
     assert ok.all()
     for i in range(0, n, 17):
