@@ -118,7 +118,7 @@ def test_roundtrip_full_size_properties(E, gpu):
     assert (out == pages).all()
     lens = np.array([len(b) for b in blocks])
     assert (lens[0::4] == 65794).mean() > 0.9   # R: incompressible (a stray 4-byte match is possible)
-    assert (lens[2::4] <= 270).all()            # Z chunks
+    assert (lens[2::4] <= 300).all()            # Z chunks
     assert len({(int(a), int(b)) for a, b in fps}) == count
 
 
