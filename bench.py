@@ -241,17 +241,25 @@ def run_ours(args):
     stream = torch.cuda.ExternalStream(eng.stream(), device=torch.device("cuda", local))
     sync_all = (lambda: (dist.barrier(), torch.cuda.synchronize())) if dist else torch.cuda.synchronize
 
-    def exchange(lens):
-        """multi-GPU: one all-gather of this step's new key records {u, l, len|rank, seq}."""
+    from edge_fuse_b200 import sharding
+    step_counter = [0]
+
+    def begin_step():
+        """Global stream positions of this step's chunks: chunk i of rank r is position
+        base + r + world*i (round-robin sharding), which is also its last-writer-wins sequence."""
+        base = 1 + step_counter[0] * world * n
+        step_counter[0] += 1
+        eng.set_stream_order(base + rank, world)
+        return sharding.shard_positions(rank, world, n, base)
+
+    def exchange(u, l, pos, lens):
+        """multi-GPU: ONE all-gather (NCCL over NVLink) of this step's key records, then the
+        other ranks' records go into the local index replica."""
         if not dist:
             return
-        rec = np.empty((n, 4), dtype=np.int64)
-        rec[:, 0] = nh.view(np.int64); rec[:, 1] = page_no.view(np.int64)
-        rec[:, 2] = lens.astype(np.int64) | (rank << 32); rec[:, 3] = cids.view(np.int64)
-        t = torch.from_numpy(rec).cuda(non_blocking=True)
-        out = torch.empty((world, n, 4), dtype=torch.int64, device="cuda")
-        dist.all_gather_into_tensor(out, t)
-        return out
+        rec = torch.from_numpy(sharding.pack_records(u, l, pos, rank, lens)).cuda(non_blocking=True)
+        gathered = sharding.all_gather_records(rec)
+        sharding.import_gathered(eng, gathered, rank)
 
     def addr_for(step: int, lane: int):
         # fresh addresses every step: genid = step (low 20 bits kept, cachemap.c:163)
@@ -271,10 +279,11 @@ def run_ours(args):
             st0 = eng.stats()
             t_wall0 = time.perf_counter()
         u, l = addr_for(it, 0)
+        pos = begin_step()
         if it >= args.warmup:
             ev[it - args.warmup][0].record(stream)
         lens = eng.put(u, l, d_pages, ts=ts, on_dev=True)
-        exchange(lens)
+        exchange(u, l, pos, lens)
         if it >= args.warmup:
             ev[it - args.warmup][1].record(stream)
     sync_all()
@@ -297,8 +306,9 @@ def run_ours(args):
         u, l = addr_for(it, 1)
         sync_all()
         t0 = time.perf_counter()
+        pos = begin_step()
         lens_e = eng.put(u, l, h_ptr, ts=ts, on_dev=False)
-        exchange(lens_e)
+        exchange(u, l, pos, lens_e)
         sync_all()
         if it >= args.warmup:
             e2e_t.append(time.perf_counter() - t0)
@@ -325,6 +335,7 @@ def run_ours(args):
                 "read_form_frac": n * CHUNK * args.steps / (enc_ns * 1e-9) / 1e9 / peak if enc_ns else 0.0,
                 "stored_ratio": stored / (n * CHUNK)}
     launches = (st1["kernel_launches"] - st0["kernel_launches"]) // args.steps
+    final = eng.stats()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -348,6 +359,8 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(n * 4)},
             "gpu_launches": int(launches * args.steps), "gpu_launches_per_step": int(launches),
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "index": {"local_entries": final["entries"], "remote_entries": final["remote_entries"],
+                      "exchange": "1 all-gather of 32-byte key records per step (NCCL)" if dist else "none (single GPU)"},
             "parity_spot_check": spot_check(eng, E, h_pages.reshape(n, CHUNK), nh, page_no, total_steps),
         }
         print(json.dumps(line))

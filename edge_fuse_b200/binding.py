@@ -10,7 +10,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-MISS, HIT, INVALID, BAD_ENTRY, BAD_DECODE = 0, 1, 2, 3, 4
+MISS, HIT, INVALID, BAD_ENTRY, BAD_DECODE, REMOTE = 0, 1, 2, 3, 4, 5
 FINGERPRINT = 1
 
 # every symbol the headers in include/ declare (checked by tests/test_abi.py)
@@ -29,6 +29,7 @@ EXPORTED_SYMBOLS = [
     "cmb200_put_batch", "cmb200_put_batch_dev", "cmb200_get_batch", "cmb200_get_batch_dev",
     "cmb200_unset_batch", "cmb200_entries", "cmb200_sample", "cmb200_read_records",
     "cmb200_read_fingerprints", "cmb200_get_stats", "cmb200_compose_keys",
+    "cmb200_set_stream_order", "cmb200_import_remote", "cmb200_locate_batch",
     "cmb200_lz4_encode_batch", "cmb200_lz4_decode_batch", "cmb200_fingerprint_batch",
     "cmb200_gen_chunk_host", "cmb200_gen_chunks_dev", "cmb200_gen_stream_ids", "cmb200_gen_addr",
 ]
@@ -43,7 +44,7 @@ class Config(C.Structure):
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "entries", "table_slots", "tombstones", "arena_bytes", "arena_used", "arena_garbage",
-        "dropped_puts", "put_chunks", "get_requests", "get_hits", "kernel_launches",
+        "dropped_puts", "remote_entries", "put_chunks", "get_requests", "get_hits", "kernel_launches",
         "encode_kernel_ns", "encode_kernel_launches", "decode_kernel_ns", "decode_kernel_launches")]
 
 
@@ -105,6 +106,9 @@ def lib() -> C.CDLL:
         "cmb200_read_records": (i32, [vp, sz, vp, vp, sz, vp]),
         "cmb200_read_fingerprints": (i32, [vp, sz, vp, vp, vp]),
         "cmb200_get_stats": (i32, [vp, vp]),
+        "cmb200_set_stream_order": (i32, [vp, u64, u64]),
+        "cmb200_import_remote": (i32, [vp, sz, vp, vp, vp, i32]),
+        "cmb200_locate_batch": (i32, [vp, sz, vp, vp, vp]),
         "cmb200_compose_keys": (i32, [i32, sz, vp, vp, vp, i32, vp, vp, vp]),
         "cmb200_lz4_encode_batch": (i32, [i32, vp, sz, u32, sz, i32, vp, sz, vp, vp]),
         "cmb200_lz4_decode_batch": (i32, [i32, vp, sz, vp, sz, u32, vp, vp]),
@@ -312,6 +316,24 @@ class Engine:
         _check(lib().cmb200_read_fingerprints(self.h, n, _ptr(addr), _ptr(fps), _ptr(ok)),
                "cmb200_read_fingerprints")
         return fps, ok
+
+    def set_stream_order(self, next_seq: int, stride: int):
+        _check(lib().cmb200_set_stream_order(self.h, next_seq, stride), "cmb200_set_stream_order")
+
+    def import_remote(self, u, l, owner, seq):
+        addr = _addr_array(u, l)
+        owner = np.ascontiguousarray(owner, dtype=np.uint32)
+        seq = np.ascontiguousarray(seq, dtype=np.uint64)
+        _check(lib().cmb200_import_remote(self.h, len(addr), _ptr(addr), _ptr(owner), _ptr(seq), 0),
+               "cmb200_import_remote")
+
+    def locate(self, u, l):
+        addr = _addr_array(u, l)
+        status = np.zeros(len(addr), dtype=np.int32)
+        owner = np.zeros(len(addr), dtype=np.uint64)
+        _check(lib().cmb200_locate_batch(self.h, len(addr), _ptr(addr), _ptr(status), _ptr(owner)),
+               "cmb200_locate_batch")
+        return status, owner
 
     def stats(self) -> dict:
         s = Stats()

@@ -50,7 +50,8 @@ struct cmb200_engine {
 	int32_t *d_lens = nullptr, *d_status = nullptr;
 	uint64_t *d_fps = nullptr, *d_recoff = nullptr;
 	unsigned int *d_work = nullptr;
-	unsigned long long seq = 1;
+	unsigned long long seq = 1;          // sequence of the next chunk
+	unsigned long long seq_stride = 1;   // > 1 when the global stream is sharded round-robin over ranks
 	// per-launch device timing of the dominant kernels (roofline evidence for bench.py)
 	static constexpr int RING = 64;
 	cudaEvent_t t0[RING] = {}, t1[RING] = {};
@@ -155,6 +156,7 @@ extern "C" cmb200_engine *cmb200_engine_create(const cmb200_config *cfg) {
 		e->arena.head = e->d_counters + 2;
 		e->arena.garbage = e->d_counters + 3;
 		e->arena.dropped = e->d_counters + 4;
+		e->table.remote = e->d_counters + 5;
 
 		e->stage_stride = ((uint64_t)e->bsize + 1024 + 15) & ~15ull;        // filemap.c:120 dest[bsize+1024]
 		ENG_CHECK(cudaMalloc(&e->d_pages[0], B * e->bsize + 256));
@@ -253,7 +255,7 @@ static int put_impl(cmb200_engine *e, size_t n, const cmb200_addr *addr, const u
 		CMB_CHECK(cudaMemcpyAsync(e->d_addr, addr + at, (size_t)m * 16, cudaMemcpyHostToDevice, e->st));
 		if (valid) CMB_CHECK(cudaMemcpyAsync(e->d_valid, valid + at, m, cudaMemcpyHostToDevice, e->st));
 		if (ts) CMB_CHECK(cudaMemcpyAsync(e->d_ts, ts + at, (size_t)m * 8, cudaMemcpyHostToDevice, e->st));
-		if (launch_upsert(e->table, e->d_addr, valid ? e->d_valid : nullptr, m, e->seq, e->d_slot, e->st)) return -1;
+		if (launch_upsert(e->table, e->d_addr, valid ? e->d_valid : nullptr, m, e->seq, e->seq_stride, e->d_slot, e->st)) return -1;
 		EncodeJob job{};
 		job.pages = d_in; job.page_stride = e->bsize; job.nbytes = e->bsize; job.n = m;
 		job.accel = (uint32_t)e->accel;
@@ -264,14 +266,14 @@ static int put_impl(cmb200_engine *e, size_t n, const cmb200_addr *addr, const u
 		job.slot_idx = e->d_slot;
 		job.addr = e->d_addr;
 		job.ts = ts ? e->d_ts : nullptr;
-		job.seq0 = e->seq;
+		job.seq0 = e->seq; job.seq_stride = e->seq_stride;
 		job.table = e->table; job.arena = e->arena;
 		CMB_CHECK(cudaEventRecord(e->t0[nb % e->RING], e->st));
 		if (launch_encode(job, e->st)) return -1;
 		CMB_CHECK(cudaEventRecord(e->t1[nb % e->RING], e->st));
 		if (!pages_on_dev) CMB_CHECK(cudaEventRecord(e->consumed[buf], e->st));
 		if (lens_out) CMB_CHECK(cudaMemcpyAsync(lens_out + at, e->d_lens, (size_t)m * 4, cudaMemcpyDeviceToHost, e->st));
-		e->seq += m;
+		e->seq += (unsigned long long)m * e->seq_stride;
 		e->stats.kernel_launches += 2;
 		// addr/valid/ts host arrays of the NEXT sub-batch are copied with cudaMemcpyAsync from
 		// pageable memory, which returns only after staging: no lifetime issue for the caller.
@@ -299,7 +301,7 @@ extern "C" int cmb200_put_batch_dev(cmb200_engine *e, size_t n, const cmb200_add
 // ---- get ---------------------------------------------------------------------------------
 
 static int get_impl(cmb200_engine *e, size_t n, const cmb200_addr *addr, const uint8_t *valid,
-    uint8_t *pages_out, bool out_on_dev, int32_t *status_out) {
+    uint8_t *pages_out, bool out_on_dev, int32_t *status_out, uint64_t *owner_out = nullptr) {
 	std::lock_guard<std::mutex> g(e->mu);
 	CMB_CHECK(cudaSetDevice(e->device));
 	const size_t B = e->max_batch;
@@ -320,6 +322,7 @@ static int get_impl(cmb200_engine *e, size_t n, const cmb200_addr *addr, const u
 		if (launch_decode(job, e->st)) return -1;
 		CMB_CHECK(cudaEventRecord(e->t1[nb % e->RING], e->st));
 		CMB_CHECK(cudaMemcpyAsync(status_out + at, e->d_status, (size_t)m * 4, cudaMemcpyDeviceToHost, e->st));
+		if (owner_out) CMB_CHECK(cudaMemcpyAsync(owner_out + at, e->d_recoff, (size_t)m * 8, cudaMemcpyDeviceToHost, e->st));
 		if (!out_on_dev) {
 			CMB_CHECK(cudaEventRecord(e->landed[buf], e->st));
 			CMB_CHECK(cudaStreamWaitEvent(e->copy, e->landed[buf], 0));
@@ -348,9 +351,56 @@ extern "C" int cmb200_get_batch(cmb200_engine *e, size_t n, const cmb200_addr *a
     void *pages_out_host, int32_t *status_out) {
 	return get_impl(e, n, addr, valid, (uint8_t *)pages_out_host, false, status_out);
 }
+extern "C" int cmb200_locate_batch(cmb200_engine *e, size_t n, const cmb200_addr *addr, int32_t *status_out,
+    uint64_t *owner_out) {
+	// lookup only: which requests hit here, miss, or live on another rank (owner_out = rank)
+	std::lock_guard<std::mutex> g(e->mu);
+	CMB_CHECK(cudaSetDevice(e->device));
+	for (size_t at = 0; at < n; at += e->max_batch) {
+		uint32_t m = (uint32_t)((n - at < e->max_batch) ? n - at : e->max_batch);
+		CMB_CHECK(cudaMemcpyAsync(e->d_addr, addr + at, (size_t)m * 16, cudaMemcpyHostToDevice, e->st));
+		if (launch_lookup(e->table, e->d_addr, nullptr, m, e->d_status, e->d_recoff, e->d_vlen, nullptr, e->st)) return -1;
+		CMB_CHECK(cudaMemcpyAsync(status_out + at, e->d_status, (size_t)m * 4, cudaMemcpyDeviceToHost, e->st));
+		CMB_CHECK(cudaMemcpyAsync(owner_out + at, e->d_recoff, (size_t)m * 8, cudaMemcpyDeviceToHost, e->st));
+		e->stats.kernel_launches++;
+	}
+	CMB_CHECK(cudaStreamSynchronize(e->st));
+	return 0;
+}
 extern "C" int cmb200_get_batch_dev(cmb200_engine *e, size_t n, const cmb200_addr *addr, const uint8_t *valid,
     void *pages_out_dev, int32_t *status_out) {
 	return get_impl(e, n, addr, valid, (uint8_t *)pages_out_dev, true, status_out);
+}
+
+// ---- multi-GPU index replication -------------------------------------------------------------
+
+extern "C" int cmb200_set_stream_order(cmb200_engine *e, uint64_t next_seq, uint64_t stride) {
+	std::lock_guard<std::mutex> g(e->mu);
+	if (stride == 0) { set_error_msg("stream order: stride must be >= 1"); return -1; }
+	e->seq = next_seq; e->seq_stride = stride;
+	return 0;
+}
+
+extern "C" int cmb200_import_remote(cmb200_engine *e, size_t n, const cmb200_addr *addr, const uint32_t *owner,
+    const uint64_t *seq, int on_dev) {
+	std::lock_guard<std::mutex> g(e->mu);
+	CMB_CHECK(cudaSetDevice(e->device));
+	for (size_t at = 0; at < n; at += e->max_batch) {
+		uint32_t m = (uint32_t)((n - at < e->max_batch) ? n - at : e->max_batch);
+		const unsigned long long *d_a; const uint32_t *d_o; const unsigned long long *d_s;
+		if (on_dev) {
+			d_a = (const unsigned long long *)(addr + at); d_o = owner + at; d_s = (const unsigned long long *)(seq + at);
+		} else {
+			CMB_CHECK(cudaMemcpyAsync(e->d_addr, addr + at, (size_t)m * 16, cudaMemcpyHostToDevice, e->st));
+			CMB_CHECK(cudaMemcpyAsync(e->d_vlen, owner + at, (size_t)m * 4, cudaMemcpyHostToDevice, e->st));
+			CMB_CHECK(cudaMemcpyAsync(e->d_ts, seq + at, (size_t)m * 8, cudaMemcpyHostToDevice, e->st));
+			d_a = e->d_addr; d_o = e->d_vlen; d_s = e->d_ts;
+		}
+		if (launch_import(e->table, e->arena, d_a, d_o, d_s, m, e->d_slot, e->st)) return -1;
+		e->stats.kernel_launches += 2;
+	}
+	CMB_CHECK(cudaStreamSynchronize(e->st));
+	return 0;
 }
 
 // ---- unset / entries / sample / records ----------------------------------------------------
@@ -388,7 +438,7 @@ extern "C" int cmb200_get_stats(cmb200_engine *e, cmb200_stats *out) {
 	if (read_counters(e, c)) return -1;
 	*out = e->stats;
 	out->entries = c[0]; out->tombstones = c[1]; out->arena_used = c[2]; out->arena_garbage = c[3];
-	out->dropped_puts = c[4];
+	out->dropped_puts = c[4]; out->remote_entries = c[5];
 	out->table_slots = e->table.cap; out->arena_bytes = e->arena.size;
 	return 0;
 }

@@ -114,14 +114,14 @@ __global__ void k_compose(const uint64_t *offset, const uint64_t *nhid, const ui
 // highest sequence per key is the one whose record survives (sequential last-writer-wins,
 // SURVEY.md App. B rule 4).
 __global__ void k_upsert(TableView t, const unsigned long long *addr, const uint8_t *valid, uint32_t n,
-    unsigned long long seq0, uint32_t *slot_idx) {
+    unsigned long long seq0, unsigned long long seq_stride, uint32_t *slot_idx) {
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	uint32_t idx = 0xffffffffu;
 	if (!valid || valid[i]) {
 		unsigned long long key = fnv_addr(addr[2 * i], addr[2 * i + 1]);
 		idx = table_find_or_claim(t, key);
-		if (idx != 0xffffffffu) atomicMax(&t.slots[idx].seq, seq0 + i);
+		if (idx != 0xffffffffu) atomicMax(&t.slots[idx].seq, seq0 + seq_stride * i);
 	}
 	slot_idx[i] = idx;
 }
@@ -147,6 +147,8 @@ __global__ void k_lookup(TableView t, const unsigned long long *addr, const uint
 				} else {
 					st = ST_BAD_ENTRY;
 				}
+			} else if (s.owner != 0 && s.addr_u == u && s.addr_l == l) {
+				st = ST_REMOTE; off = s.owner - 1;
 			}
 		}
 	}
@@ -169,6 +171,7 @@ __global__ void k_unset(TableView t, ArenaView a, const unsigned long long *addr
 	atomicAdd(t.entries, (unsigned long long)-1ll);
 	atomicAdd(a.garbage, (unsigned long long)s.alloc);
 	s.alloc = 0;
+	s.owner = 0;
 	if (idx < t.cap) {
 		s.key = KEY_TOMB;
 		atomicAdd(t.tombs, 1ull);
@@ -245,6 +248,7 @@ __device__ void commit_record(const EncodeJob &job, uint32_t i, uint32_t idx, co
 	else warp_copy_rw(rec + 24, payload, plen, lane);
 	__syncwarp();
 	if (lane == 0) {
+		if (s.owner) { atomicAdd(job.table.remote, (unsigned long long)-1ll); s.owner = 0; }   // now newest here
 		s.addr_u = au; s.addr_l = al;
 		s.ts = job.ts ? job.ts[i] : 0;
 		if (job.table.fp) { job.table.fp[2 * (size_t)idx] = fp_hi; job.table.fp[2 * (size_t)idx + 1] = fp_lo; }
@@ -268,7 +272,7 @@ __global__ void __launch_bounds__(512, 1) k_encode(EncodeJob job) {
 		if (store) {
 			idx = job.slot_idx[i];
 			// invalid address, or a later chunk of this batch rewrites the same key
-			bool live = idx != 0xffffffffu && job.table.slots[idx].seq == job.seq0 + i;
+			bool live = idx != 0xffffffffu && job.table.slots[idx].seq == job.seq0 + job.seq_stride * i;
 			if (!live) { if (lane == 0) job.lens[i] = -1; continue; }
 		}
 		const uint8_t *src = job.pages + (size_t)i * job.page_stride;
@@ -426,10 +430,46 @@ int launch_compose(const uint64_t *offset, const uint64_t *nhid, const uint32_t 
 	CMB_CHECK(cudaGetLastError());
 	return 0;
 }
-int launch_upsert(TableView t, const unsigned long long *addr, const uint8_t *valid, uint32_t n,
-    unsigned long long seq0, uint32_t *slot_idx, cudaStream_t st) {
+// Multi-GPU import, phase 1: claim the slot and record stream order; phase 2: the newest
+// sequence per key applies itself (a key may appear several times in one import).
+__global__ void k_import_claim(TableView t, const unsigned long long *addr, const unsigned long long *seq,
+    uint32_t n, uint32_t *slot_idx) {
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	uint32_t idx = table_find_or_claim(t, fnv_addr(addr[2 * i], addr[2 * i + 1]));
+	if (idx != 0xffffffffu) atomicMax(&t.slots[idx].seq, seq[i]);
+	slot_idx[i] = idx;
+}
+__global__ void k_import_apply(TableView t, ArenaView a, const unsigned long long *addr, const uint32_t *owner,
+    const unsigned long long *seq, uint32_t n, const uint32_t *slot_idx) {
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	uint32_t idx = slot_idx[i];
+	if (idx == 0xffffffffu) return;
+	Slot &s = t.slots[idx];
+	if (s.seq != seq[i]) return;                 // an even newer put (local or imported) owns the key
+	if (s.vlen) {                                // our local record is superseded
+		atomicAdd(t.entries, (unsigned long long)-1ll);
+		atomicAdd(a.garbage, (unsigned long long)s.alloc);
+		s.vlen = 0; s.alloc = 0;
+	}
+	if (s.owner == 0) atomicAdd(t.remote, 1ull);
+	s.owner = (unsigned long long)owner[i] + 1;
+	s.addr_u = addr[2 * i]; s.addr_l = addr[2 * i + 1];
+}
+int launch_import(TableView t, ArenaView a, const unsigned long long *addr, const uint32_t *owner,
+    const unsigned long long *seq, uint32_t n, uint32_t *slot_idx, cudaStream_t st) {
 	if (n == 0) return 0;
-	k_upsert<<<GRID1D(n), 0, st>>>(t, addr, valid, n, seq0, slot_idx);
+	k_import_claim<<<GRID1D(n), 0, st>>>(t, addr, seq, n, slot_idx);
+	CMB_CHECK(cudaGetLastError());
+	k_import_apply<<<GRID1D(n), 0, st>>>(t, a, addr, owner, seq, n, slot_idx);
+	CMB_CHECK(cudaGetLastError());
+	return 0;
+}
+int launch_upsert(TableView t, const unsigned long long *addr, const uint8_t *valid, uint32_t n,
+    unsigned long long seq0, unsigned long long seq_stride, uint32_t *slot_idx, cudaStream_t st) {
+	if (n == 0) return 0;
+	k_upsert<<<GRID1D(n), 0, st>>>(t, addr, valid, n, seq0, seq_stride, slot_idx);
 	CMB_CHECK(cudaGetLastError());
 	return 0;
 }

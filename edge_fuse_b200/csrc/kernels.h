@@ -17,7 +17,7 @@ struct Slot {
 	uint32_t alloc;              // arena bytes reserved at rec_off
 	unsigned long long ts;       // LMDB node attribute of the reference
 	unsigned long long seq;      // stream order of the last put that claimed this key
-	unsigned long long spare;
+	unsigned long long owner;    // 0 = record (if any) is in this GPU's arena; r+1 = key last written on rank r
 };
 static_assert(sizeof(Slot) == 64, "slot layout");
 
@@ -29,6 +29,7 @@ struct TableView {
 	uint64_t cap;                // power of two
 	unsigned long long *entries; // live records
 	unsigned long long *tombs;   // deleted main-table slots (rebuild trigger)
+	unsigned long long *remote;  // keys whose newest record lives on another GPU
 	uint64_t *fp;                // optional, 2 x u64 per slot {hi, lo}
 };
 
@@ -46,6 +47,7 @@ enum LookupStatus : int32_t {
 	ST_INVALID = 2,      // page number overflowed 44 bits: not counted as a request (cachemap.c:173-174)
 	ST_BAD_ENTRY = 3,    // key present with another address (filemap.c:236-240)
 	ST_BAD_DECODE = 4,   // decoder consumed != stored length (filemap.c:244-248)
+	ST_REMOTE = 5,       // multi-GPU: the key's newest record is on another rank (status - 5 is not encoded; see owner_out)
 };
 
 struct EncodeJob {
@@ -64,6 +66,7 @@ struct EncodeJob {
 	const unsigned long long *addr; // per chunk {u,l}
 	const unsigned long long *ts;   // per chunk
 	unsigned long long seq0;  // sequence of chunk 0
+	unsigned long long seq_stride;  // sequence step between chunks (world size when chunks are sharded round-robin)
 	TableView table;
 	ArenaView arena;
 };
@@ -94,10 +97,16 @@ int launch_compose(const uint64_t *offset, const uint64_t *nhid, const uint32_t 
     uint32_t n, unsigned long long *addr, uint8_t *valid, unsigned long long *key, cudaStream_t st);
 
 int launch_upsert(TableView t, const unsigned long long *addr, const uint8_t *valid, uint32_t n,
-    unsigned long long seq0, uint32_t *slot_idx, cudaStream_t st);
+    unsigned long long seq0, unsigned long long seq_stride, uint32_t *slot_idx, cudaStream_t st);
+
+// Multi-GPU index replication: records {addr, owner rank, seq} written on other GPUs.  Newest
+// sequence per key wins; a local record that loses is retired.
+int launch_import(TableView t, ArenaView a, const unsigned long long *addr, const uint32_t *owner,
+    const unsigned long long *seq, uint32_t n, uint32_t *slot_idx, cudaStream_t st);
 
 int launch_lookup(TableView t, const unsigned long long *addr, const uint8_t *valid, uint32_t n,
     int32_t *status, uint64_t *rec_off, uint32_t *vlen, unsigned long long *ts_out, cudaStream_t st);
+// After launch_lookup: status ST_REMOTE entries have their owner rank in rec_off[i].
 
 int launch_unset(TableView t, ArenaView a, const unsigned long long *addr, uint32_t n, cudaStream_t st);
 

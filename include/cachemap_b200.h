@@ -49,7 +49,8 @@ enum {
 	CMB200_HIT = 1,
 	CMB200_INVALID = 2,     /* address rejected: not counted as a request (cachemap.c:173-174) */
 	CMB200_BAD_ENTRY = 3,   /* key present under another address: a miss (filemap.c:236-240) */
-	CMB200_BAD_DECODE = 4   /* decoded length != stored length: a miss (filemap.c:244-248) */
+	CMB200_BAD_DECODE = 4,  /* decoded length != stored length: a miss (filemap.c:244-248) */
+	CMB200_REMOTE = 5       /* multi-GPU: the newest record of this key lives on another rank */
 };
 
 const char *cmb200_last_error(void);
@@ -102,11 +103,26 @@ int cmb200_read_fingerprints(cmb200_engine *e, size_t n, const cmb200_addr *addr
 typedef struct cmb200_stats {
 	uint64_t entries, table_slots, tombstones;
 	uint64_t arena_bytes, arena_used, arena_garbage, dropped_puts;
+	uint64_t remote_entries;  /* keys whose newest record is on another GPU (multi-GPU index) */
 	uint64_t put_chunks, get_requests, get_hits, kernel_launches;
 	/* summed CUDA-event durations of the encode / decode kernel launches (last 64 per call) */
 	uint64_t encode_kernel_ns, encode_kernel_launches, decode_kernel_ns, decode_kernel_launches;
 } cmb200_stats;
 int cmb200_get_stats(cmb200_engine *e, cmb200_stats *out);
+
+/* ---- multi-GPU: chunks sharded round-robin over ranks, one replicated key index per GPU ----
+ * Each rank puts its own shard with the chunks' GLOBAL stream positions as sequence numbers
+ * (next_seq = position of the rank's next chunk, stride = world size), then the ranks all-gather
+ * {address, owner rank, sequence} of what they stored (NCCL, done by the caller) and import the
+ * others' records: per key the highest sequence wins, exactly as sequential puts would resolve
+ * (SURVEY.md §8e "ordering caveat"); a local record that loses is retired. */
+int cmb200_set_stream_order(cmb200_engine *e, uint64_t next_seq, uint64_t stride);
+int cmb200_import_remote(cmb200_engine *e, size_t n, const cmb200_addr *addr, const uint32_t *owner,
+    const uint64_t *seq, int arrays_on_device);
+/* Lookup only: status_out[i] in CMB200_{MISS,HIT,BAD_ENTRY,REMOTE}; owner_out[i] = owning rank for
+ * CMB200_REMOTE. */
+int cmb200_locate_batch(cmb200_engine *e, size_t n, const cmb200_addr *addr, int32_t *status_out,
+    uint64_t *owner_out);
 
 /* ---- kernel-level entry points (parity tests, benchmarks); device = CUDA ordinal or -1 ---- */
 

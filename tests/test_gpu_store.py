@@ -222,3 +222,41 @@ def test_eviction_keeps_capacity(E, gpu, tmp_path):
     assert hit.sum() == entries
     assert hit[-500:].mean() > hit[:500].mean()
     cm.free()
+
+
+def test_remote_index_import(E, gpu, oracle):
+    """Multi-GPU index replica on one GPU: records written "elsewhere" are imported; per key the
+    highest stream position wins whatever the arrival order (SURVEY.md 8e ordering caveat)."""
+    eng = E.Engine(pshift=12, accel=12, capacity=4096, arena_bytes=32 << 20, max_batch=64)
+    n = 100
+    pages = np.stack([datagen.make_page("T", 4096, i) for i in range(n)])
+    u = np.full(n, 5, dtype=np.uint64)
+    l = np.arange(n, dtype=np.uint64)
+    eng.set_stream_order(1000, 2)                     # this rank owns positions 1000, 1002, ...
+    eng.put(u, l, pages)
+    assert eng.entries() == n
+    # rank 1 wrote keys 0..49 later (odd positions above ours) and keys 50..59 earlier; key 200 is new.
+    ru = np.full(61, 5, dtype=np.uint64)
+    rl = np.concatenate([np.arange(60), [200]]).astype(np.uint64)
+    rseq = np.concatenate([1001 + 2 * np.arange(50) + 2 * 200, 3 + np.arange(10), [7]]).astype(np.uint64)
+    # duplicates inside one import: key 0 appears twice, the larger sequence must win
+    ru = np.append(ru, np.uint64(5)); rl = np.append(rl, np.uint64(0)); rseq = np.append(rseq, np.uint64(5000))
+    owner = np.full(len(ru), 1, dtype=np.uint32); owner[-1] = 3
+    perm = np.argsort(datagen.words(9, len(ru)))      # arrival order must not matter
+    eng.import_remote(ru[perm], rl[perm], owner[perm], rseq[perm])
+    status, own = eng.locate(u, l)
+    assert (status[:50] == E.REMOTE).all() and (status[50:] == E.HIT).all()
+    assert own[0] == 3 and (own[1:50] == 1).all()
+    st = eng.stats()
+    assert st["entries"] == 50 and st["remote_entries"] == 51
+    s2, o2 = eng.locate(np.array([5], dtype=np.uint64), np.array([200], dtype=np.uint64))
+    assert s2[0] == E.REMOTE and o2[0] == 1
+    out, gstat = eng.get(u, l)
+    assert (gstat[:50] == E.REMOTE).all() and (gstat[50:] == E.HIT).all() and (out[50:] == pages[50:]).all()
+    # a later local put takes the key back
+    eng.set_stream_order(10_000, 2)
+    eng.put(u[:5], l[:5], pages[:5])
+    status, _ = eng.locate(u[:6], l[:6])
+    assert (status[:5] == E.HIT).all() and status[5] == E.REMOTE
+    assert eng.stats()["remote_entries"] == 46 and eng.entries() == 55
+    eng.close()

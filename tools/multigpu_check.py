@@ -1,0 +1,55 @@
+#!/usr/bin/env python
+"""2+ GPU functional check of the sharded put path (run under torchrun on the GPU box):
+every rank puts its round-robin shard of a stream with 30 % same-address repeats, the ranks
+exchange key records, and afterwards every rank's index must agree with a sequential pass:
+the newest writer of each key is HIT on its owner and REMOTE(owner) everywhere else."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import torch.distributed as dist
+
+import edge_fuse_b200 as E
+from edge_fuse_b200 import sharding
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+n_total, bs = 4096 * world, 65536
+cids, distinct = E.gen_stream_ids(n_total, 0.3)
+off, nh = E.gen_addr(42, cids, 16)
+eng = E.Engine(pshift=16, accel=12, capacity=4 * n_total, arena_bytes=n_total * bs // world + (256 << 20),
+               max_batch=1024, device=local)
+mine = np.arange(rank, n_total, world)
+u, l = nh[mine], off[mine] >> np.uint64(16)
+d = eng.dev_alloc(len(mine) * bs)
+eng.gen_chunks_dev(42, cids[mine], d)
+for b0 in range(0, len(mine), 1024):                       # several batches, one exchange each
+    sl = slice(b0, b0 + 1024)
+    pos = (1 + mine[sl]).astype(np.uint64)
+    eng.set_stream_order(int(pos[0]), world)
+    lens = eng.put(u[sl], l[sl], d + b0 * bs, on_dev=True)
+    rec = torch.from_numpy(sharding.pack_records(u[sl], l[sl], pos, rank, lens)).cuda()
+    gathered = sharding.all_gather_records(rec)
+    sharding.import_gathered(eng, gathered, rank)
+# expectation from a sequential pass over the global stream
+last = {}
+for k in range(n_total):
+    last[int(cids[k])] = k
+qc = np.array(sorted(last), dtype=np.uint64)
+qo, qn = E.gen_addr(42, qc, 16)
+status, owner = eng.locate(qn, qo >> np.uint64(16))
+exp_owner = np.array([last[int(c)] % world for c in qc])
+ok = ((status == E.HIT) == (exp_owner == rank)).all() and (owner[status == E.REMOTE] == exp_owner[status == E.REMOTE]).all() \
+    and ((status == E.HIT) | (status == E.REMOTE)).all()
+st = eng.stats()
+tot = torch.tensor([st["entries"]], device="cuda")
+dist.all_reduce(tot)
+ok = ok and int(tot.item()) == distinct and st["entries"] + st["remote_entries"] == distinct
+print(f"rank {rank}: ok={bool(ok)} local={st['entries']} remote={st['remote_entries']} distinct={distinct}", flush=True)
+flag = torch.tensor([int(ok)], device="cuda")
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+dist.destroy_process_group()
+sys.exit(0 if flag.item() == 1 else 1)
