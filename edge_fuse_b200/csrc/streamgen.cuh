@@ -2,7 +2,9 @@
 // the host generator (CPU baseline input, small tests) and the device generator (HBM-resident
 // benchmark input).  Bench / test utility; not part of the reference's API.
 //
-// Chunk `cid` of a stream seeded `seed` (default 42) has content class cid & 3:
+// Chunk `cid` of a stream seeded `seed` (default 42) has content class (cid + (cid >> 3)) & 3 (the
+// four classes take turns, and the turn order drifts every 8 chunks so that sharding chunk k to
+// GPU k mod G never pins a class to a GPU):
 //   0 R  incompressible: 8-byte words word(w) = mix(base + (w+1)*G)
 //   1 T  low-entropy text: byte j takes 16 bits r of word(j/4) (field j%4);
 //        r&3 != 0 -> 'a' + ((r>>2)&3)  (probability 3/4), else the random byte r>>8
@@ -27,6 +29,7 @@ SG_HD uint64_t sg_mix(uint64_t z) {
 	z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
 	return z ^ (z >> 31);
 }
+SG_HD uint32_t sg_class(uint64_t cid) { return (uint32_t)((cid + (cid >> 3)) & 3); }
 SG_HD uint64_t sg_base(uint64_t seed, uint64_t cid) { return sg_mix(seed ^ (cid * 0xD1B54A32D192ED03ULL)); }
 SG_HD uint64_t sg_word(uint64_t base, uint64_t w) { return sg_mix(base + (w + 1) * SG_GOLDEN); }
 SG_HD uint8_t sg_text_byte(uint64_t base, uint32_t j) {
@@ -36,7 +39,7 @@ SG_HD uint8_t sg_text_byte(uint64_t base, uint32_t j) {
 // The 8 bytes [8*w8, 8*w8+8) of chunk cid, little-endian packed.
 SG_HD uint64_t sg_chunk_word(uint64_t seed, uint64_t cid, uint32_t bsize, uint32_t w8) {
 	uint64_t base = sg_base(seed, cid);
-	uint32_t cls = (uint32_t)(cid & 3);
+	uint32_t cls = sg_class(cid);
 	if (cls == 0) return sg_word(base, w8);
 	if (cls == 2) return w8 == 0 ? (cid & 0xFFFFu) : 0;
 	uint32_t j0 = w8 * 8;

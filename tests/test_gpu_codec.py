@@ -117,8 +117,9 @@ def test_roundtrip_full_size_properties(E, gpu):
     assert (used == np.array([len(b) for b in blocks])).all()
     assert (out == pages).all()
     lens = np.array([len(b) for b in blocks])
-    assert (lens[0::4] == 65794).mean() > 0.9   # R: incompressible (a stray 4-byte match is possible)
-    assert (lens[2::4] <= 300).all()            # Z chunks
+    cls = (np.arange(count) + (np.arange(count) >> 3)) & 3
+    assert (lens[cls == 0] == 65794).mean() > 0.9   # R: incompressible (a stray 4-byte match is possible)
+    assert (lens[cls == 2] <= 300).all()            # Z chunks
     assert len({(int(a), int(b)) for a, b in fps}) == count
 
 

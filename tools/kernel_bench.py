@@ -35,7 +35,8 @@ def main():
     gen = 0
     for cls in a.classes:
         k = "RTZM".find(cls)
-        cids = (np.arange(n, dtype=np.uint64) * np.uint64(4) + np.uint64(k)) if k >= 0 else np.arange(n, dtype=np.uint64)
+        allc = np.arange(8 * n, dtype=np.uint64)
+        cids = allc[((allc + (allc >> np.uint64(3))) & np.uint64(3)) == k][:n] if k >= 0 else allc[:n]
         eng.gen_chunks_dev(42, cids, d)
         u = np.full(n, 7, dtype=np.uint64)
         best_e, best_d, lens = 1e30, 1e30, None
