@@ -257,11 +257,11 @@ __device__ void commit_record(const EncodeJob &job, uint32_t i, uint32_t idx, co
 	}
 }
 
-template <bool WIDE, uint32_t RING, bool DIRECT>
+template <bool WIDE>
 __global__ void __launch_bounds__(512, 1) k_encode(EncodeJob job) {
 	extern __shared__ __align__(16) uint8_t smem[];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	uint8_t *wsm = smem + (size_t)warp * (LZ4_TABLE_BYTES + RING);
+	uint8_t *wsm = smem + (size_t)warp * LZ4_TABLE_BYTES;
 	for (;;) {
 		uint32_t i = 0;
 		if (lane == 0) i = atomicAdd(job.work, 1u);
@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(512, 1) k_encode(EncodeJob job) {
 			continue;
 		}
 		uint8_t *dst = job.stage + (size_t)i * job.stage_stride;
-		uint32_t clen = lz4_encode_warp<WIDE, RING, DIRECT>(src, job.nbytes, dst, job.accel, wsm, lane);
+		uint32_t clen = lz4_encode_warp<WIDE>(src, job.nbytes, dst, job.accel, wsm, lane);
 		if (lane == 0) job.lens[i] = (int32_t)clen;
 		if (store) {
 			__syncwarp();
@@ -314,28 +314,14 @@ static int env_int(const char *name, int dflt, int lo, int hi) {
 	return x < lo ? lo : x > hi ? hi : x;
 }
 
-typedef void (*encode_kernel_t)(EncodeJob);
-
 int launch_encode(const EncodeJob &job, cudaStream_t st) {
 	if (job.n == 0) return 0;
-	// Residency is bounded by shared memory: (16 KiB position table + RING bytes of page window)
-	// per chunk, warps/CTA x CTAs/SM of them in the 227 KiB of an SM.
-	static int ring = env_int("CMB200_ENC_RING", 0, 0, 8192);   // 0 = no window (page read from global memory)
-	static int ctas = env_int("CMB200_ENC_CTAS_PER_SM", 1, 1, 8);
-	const bool direct = job.accel > 12 || ring == 0;
-	const int ring_b = direct ? 0 : ring >= 8192 ? 8192 : ring >= 4096 ? 4096 : 2048;
-	const int per_warp = (int)LZ4_TABLE_BYTES + ring_b;
-	static int warps_env = env_int("CMB200_ENC_WARPS", 0, 0, 16);
-	int warps = warps_env ? warps_env : (227 * 1024 / ctas - 1024) / per_warp;
-	if (warps > 16) warps = 16;
-	if (warps < 1) warps = 1;
-	size_t smem = (size_t)warps * per_warp;
-	const bool wide = job.nbytes >= LZ4_NARROW_LIMIT;
-	encode_kernel_t kern;
-	if (direct) kern = wide ? k_encode<true, 0, true> : k_encode<false, 0, true>;
-	else if (ring_b == 8192) kern = wide ? k_encode<true, 8192, false> : k_encode<false, 8192, false>;
-	else if (ring_b == 4096) kern = wide ? k_encode<true, 4096, false> : k_encode<false, 4096, false>;
-	else kern = wide ? k_encode<true, 2048, false> : k_encode<false, 2048, false>;
+	// Residency is bounded by shared memory: one 16 KiB position table per chunk, 14 of them in
+	// the 227 KiB of an SM (2 CTAs x 7 warps); grid = 2 CTAs per SM, chunks handed out dynamically.
+	static int warps = env_int("CMB200_ENC_WARPS", 7, 1, 14);
+	static int ctas = env_int("CMB200_ENC_CTAS_PER_SM", 2, 1, 8);
+	size_t smem = (size_t)warps * LZ4_TABLE_BYTES;
+	auto kern = job.nbytes >= LZ4_NARROW_LIMIT ? k_encode<true> : k_encode<false>;
 	CMB_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	CMB_CHECK(cudaMemsetAsync(job.work, 0, sizeof(unsigned int), st));
 	uint32_t grid = (uint32_t)(sm_count() * ctas);

@@ -6,29 +6,30 @@
 // (byU16 + 13-bit hash4 for n < 65547, byU32 + 12-bit hash5 + MAX_DISTANCE test otherwise).
 //
 // The greedy parse is a serial dependency chain per chunk (every probe reads then writes the
-// position table), so throughput = chunks in flight / latency per LZ4 sequence:
-//   * one independent chunk per warp; per warp only the 16 KiB position table and a small sliding
-//     window of the page (RING bytes: ~1 KiB ahead of the parse position, the rest behind it) live
-//     in shared memory, so 9-11 chunks are resident per SM.  The window is filled 512 bytes at a
-//     time with cp.async (global -> shared, no registers) one block ahead of need; probe reads,
-//     literal bytes and most match candidates (LZ4 matches are mostly recent) are then
-//     shared-memory reads.  Candidates older than the window fall back to ld.global.nc.
-//     Staging the whole 64 KiB page would cap residency at two chunks per SM.
-//   * inside a chunk the warp runs the reference's loop speculatively, one LZ4 sequence per
-//     iteration and two dependent memory round trips per sequence:
-//       step 1 "unified batch": lane 0 replays the table refill of position end-2 (lz4.c:691),
-//         lane 1 the immediate re-test at `end` (lz4.c:694-707), lanes 2.. the first 30 probes of
-//         the following search (lz4.c:593-619; probe positions are a closed form of the probe
-//         index: +1, then +accel for 64 probes, +accel+1 for the next 64, ...).  All are "read
-//         slot, write slot, compare 4 bytes" in program order.  Every lane stores its position
-//         speculatively and reads the slot back: if all 32 see their own value no two lanes share
-//         a slot, program order is irrelevant, the first hit (ballot) wins and lanes past the
-//         winner put the old value back.  A clash (two lanes, one slot) or a search that needs
-//         more than 30 probes goes to lz4_search_slow, which resolves program order with
-//         __match_any_sync.
-//       step 2 "extend": lanes 0-15 count the match forward (lz4.c:415-439) while lanes 16-31
-//         catch up backward (lz4.c:622), one ballot for both.
-//   * the hot loop is kept small on purpose (the profile of the first version showed a third of
+// position table), so throughput = chunks in flight / latency per LZ4 sequence.
+//   * Chunks in flight: one independent chunk per warp; only the 16 KiB position table lives in
+//     shared memory, 14 chunks per SM.  The page is read from HBM through the read-only L1 path
+//     (ld.global.nc): it is immutable, probes walk it forward and LZ4 candidates are mostly
+//     recent, so the 128-byte lines get reused.  Staging the whole 64 KiB page in shared memory
+//     would cap residency at two chunks per SM; a 2-8 KiB cp.async sliding window per warp was
+//     built and measured slower than spending the same shared memory on more resident chunks
+//     (DESIGN.md §4).
+//   * Latency per sequence: the warp runs the reference's loop speculatively, one LZ4 sequence
+//     per iteration with ONE table round trip and ONE page round trip:
+//       "unified batch": lane 0 replays the table refill of position end-2 (lz4.c:691), lane 1
+//         the immediate re-test at `end` (lz4.c:694-707), lanes 2.. the first 30 probes of the
+//         following search (lz4.c:593-619; probe positions are a closed form of the probe index:
+//         +1, then +accel for 64 probes, +accel+1 for the next 64, ...).  All are "read slot,
+//         write slot, compare 4 bytes" in program order.  Every lane stores its position
+//         speculatively and reads the slot back; lanes that see a foreign value share a slot
+//         with another lane.  Below the lowest such lane program order is irrelevant, so if the
+//         first hit (ballot) lies there it wins and the later lanes put the old values back.
+//         Otherwise (a true intra-batch dependency, or 30 probes were not enough) the general
+//         search lz4_search_slow resolves program order with __match_any_sync.
+//       Each lane fetches 16 bytes around its probe and around its candidate in that same round
+//         trip, so the winner already knows the match extension up to 8 bytes forward
+//         (lz4.c:415-439) and 4 bytes backward (lz4.c:622); longer ones go out of line.
+//   * The hot loop is kept small on purpose (the profile of the first version showed a third of
 //     the stall samples waiting on instruction fetch): rare paths are __noinline__.
 #pragma once
 #include "common.cuh"
@@ -67,65 +68,21 @@ template <> struct Lz4Table<true> {
 	__device__ __forceinline__ void put(uint32_t h, uint32_t pos) const { t[h] = pos; }
 };
 
-// ---- sliding window -----------------------------------------------------------------------
-
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
-	uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
-	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() {
-	asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
-}
-
-// Window of the page in shared memory: byte p of the page lives at ring[p & (RING-1)] for
-// lo <= p < done.  Blocks of 512 bytes are appended with cp.async one block ahead of need; all
-// but the newest block are complete after a refill.  State is three scalars kept in registers.
-constexpr uint32_t LZ4_AHEAD = 448;   // bytes past p0 one sequence may touch (accel <= 12): 30 probes + 64-byte count
-
-struct Lz4Win { uint32_t lo, hi, done; };
-
-// Makes [p0 - 3, p0 + LZ4_AHEAD) resident.  Normally appends one block; after a long match it
-// restarts the window around p0, keeping as much history as fits.  Out of line: runs once per
-// ~512 bytes of progress.  Returns lo | hi << 21 | done << 42.
-template <uint32_t RING>
-__device__ __noinline__ uint64_t lz4_window_refill(const uint8_t *src, uint8_t *ring, uint32_t n16,
-    uint32_t lo, uint32_t hi, uint32_t p0, int lane) {
-	const uint32_t want = (p0 + LZ4_AHEAD + 511u) & ~511u;
-	if (p0 >= hi + 3u || p0 < lo + 3u) {                              // nothing useful resident
-		// at most RING/512 blocks may be in flight at once: two copies into one ring slot would race
-		const uint32_t back = (p0 - 3u) & ~511u, hist = RING - 1536u;
-		lo = back > hist ? back - hist : 0u;
-		hi = lo;
-		__syncwarp();
-	}
-	const uint32_t last = ((n16 + 511u) & ~511u) + 512u;             // blocks past the page are empty
-	while (hi < want + 512u && hi < last) {
-		const uint32_t p = hi + 16u * lane;
-		if (p < n16) cp_async16(ring + (p & (RING - 1)), src + p);
-		cp_async_commit();
-		hi += 512u;
-		if (hi - lo > RING) lo = hi - RING;
-	}
-	uint32_t done;
-	if (hi >= want + 512u) { cp_async_wait<1>(); done = hi - 512u; } else { cp_async_wait<0>(); done = hi; }
-	__syncwarp();
-	return (uint64_t)lo | ((uint64_t)hi << 21) | ((uint64_t)done << 42);
-}
-
-template <uint32_t RING>
-__device__ __forceinline__ uint32_t ring32(const uint8_t *ring, uint32_t p) {
-	if (RING == 0) return 0;
-	const uint32_t o = p & (RING - 1) & ~3u;
-	const uint32_t w0 = *reinterpret_cast<const uint32_t *>(ring + o);
-	const uint32_t w1 = *reinterpret_cast<const uint32_t *>(ring + ((o + 4u) & (RING - 1)));
-	return __funnelshift_r(w0, w1, (p & 3u) * 8u);
-}
-// Unaligned 4 bytes from the page in global memory; the word after the last one is readable
-// (page buffers are padded), so no bounds predicate.
-__device__ __forceinline__ uint32_t glob32(const uint8_t *src, uint32_t p) {
-	const uint32_t *q = reinterpret_cast<const uint32_t *>(src + (p & ~3u));
-	return __funnelshift_r(__ldg(q), __ldg(q + 1), (p & 3u) * 8u);
+// The 16 bytes [p-4, p+12) of the page as four little-endian words {before, at, next, next2}.
+// Five aligned loads (page buffers are padded past their end; the word before the page start is
+// never needed because backward extension is capped by the position itself).
+struct Lz4Around { uint32_t before, at, next, next2; };
+__device__ __forceinline__ Lz4Around lz4_around(const uint8_t *src, uint32_t p) {
+	const uint32_t a = p & ~3u, sh = (p & 3u) * 8u;
+	const uint32_t *q = reinterpret_cast<const uint32_t *>(src + a);
+	const uint32_t w0 = a ? __ldg(q - 1) : 0u;
+	const uint32_t w1 = __ldg(q), w2 = __ldg(q + 1), w3 = __ldg(q + 2), w4 = __ldg(q + 3);
+	Lz4Around r;
+	r.before = __funnelshift_r(w0, w1, sh);
+	r.at = __funnelshift_r(w1, w2, sh);
+	r.next = __funnelshift_r(w2, w3, sh);
+	r.next2 = __funnelshift_r(w3, w4, sh);
+	return r;
 }
 
 // ---- rare paths, kept out of line ------------------------------------------------------------
@@ -190,9 +147,8 @@ __device__ __forceinline__ uint64_t lz4_pack(bool found, bool retest, uint32_t i
 	return ((uint64_t)found << 63) | ((uint64_t)retest << 62) | ((uint64_t)ip << 32) | match;
 }
 
-// The general search (any number of probes, any hash clashes), reading the page from global
-// memory.  Lanes below `shift` of the first batch are the refill / re-test lanes.  Starts at
-// batch g0 (0, or 32 when the inlined first batch found nothing).
+// The general search (any number of probes, any hash clashes).  Slot g of the search is the
+// refill (g = 0) / re-test (g = 1) when g < shift, else probe g - shift; starts at slot g0.
 template <bool WIDE>
 __device__ __noinline__ uint64_t lz4_search_slow(const uint8_t *src, uint32_t lim4, Lz4Table<WIDE> tab,
     uint32_t anchor, uint32_t shift, uint32_t accel, uint32_t mflimit, uint32_t g0, int lane) {
@@ -234,8 +190,6 @@ __device__ __noinline__ uint64_t lz4_search_slow(const uint8_t *src, uint32_t li
 	}
 }
 
-// ---- the encoder -----------------------------------------------------------------------------
-
 // Everything after a found match that does not fit the straight-line emitter: long literal runs,
 // length bytes beyond one.  Returns the new output offset.
 __device__ __noinline__ uint32_t lz4_emit_general(uint8_t *dst, uint32_t op, const uint8_t *src, uint32_t anchor,
@@ -251,19 +205,17 @@ __device__ __noinline__ uint32_t lz4_emit_general(uint8_t *dst, uint32_t op, con
 	return op;
 }
 
+// ---- the encoder -----------------------------------------------------------------------------
+
 // Encodes src[0,n) into dst; returns the block length (uniform across the warp).
-// smem: LZ4_TABLE_BYTES of table followed by RING bytes of window, 16-byte aligned.
-// src must be 16-byte aligned and readable up to 16 bytes past src+n.
-// DIRECT (accel > 12: probes of one batch span more than the look-ahead) reads the page from
-// global memory only.
-template <bool WIDE, uint32_t RING, bool DIRECT>
+// `smem` is this warp's LZ4_TABLE_BYTES of shared memory.  src must be 4-byte aligned and
+// readable up to 16 bytes past src+n (the library's page buffers are contiguous and padded).
+template <bool WIDE>
 __device__ uint32_t lz4_encode_warp(const uint8_t *__restrict__ src, uint32_t n, uint8_t *__restrict__ dst,
     uint32_t accel, uint8_t *smem, int lane) {
 	Lz4Table<WIDE> tab;
 	tab.t = reinterpret_cast<decltype(tab.t)>(smem);
-	uint8_t *ring = smem + LZ4_TABLE_BYTES;
 	const uint32_t lim4 = (n + 3u) & ~3u;
-	const uint32_t n16 = (n + 15u) & ~15u;
 	uint32_t op = 0, anchor = 0;
 
 	// lz4.c:739 — table cleared per call: an untouched slot aliases position 0.
@@ -273,7 +225,6 @@ __device__ uint32_t lz4_encode_warp(const uint8_t *__restrict__ src, uint32_t n,
 #pragma unroll 4
 		for (uint32_t i = lane; i < LZ4_TABLE_BYTES / 16; i += 32) t4[i] = z;
 	}
-	Lz4Win win = {0, 0, 0};
 	__syncwarp();
 
 	if (n >= LZ4_MIN_INPUT) {
@@ -283,50 +234,64 @@ __device__ uint32_t lz4_encode_warp(const uint8_t *__restrict__ src, uint32_t n,
 		uint32_t shift = 0;          // 2 once a match has ended: lanes 0,1 replay lz4.c:691-707
 		for (;;) {
 			const uint32_t p0 = anchor + 1;       // first probe of the search (lz4.c:584,710)
-			if (!DIRECT && (p0 + LZ4_AHEAD > win.done || p0 < win.lo + 3u)) {
-				uint64_t r = lz4_window_refill<RING>(src, ring, n16, win.lo, win.hi, shift ? p0 : 3u, lane);
-				win.lo = (uint32_t)r & 0x1fffffu; win.hi = (uint32_t)(r >> 21) & 0x1fffffu; win.done = (uint32_t)(r >> 42);
-			}
 			// speculative literal byte: src[anchor + lane] (used when the run is <= 32 bytes)
-			const uint32_t litbyte = DIRECT ? ldg8(src + min(anchor + lane, n - 1u)) : (uint32_t)ring[(anchor + lane) & (RING - 1)];
+			const uint32_t litbyte = ldg8(src + min(anchor + lane, n - 1u));
 
-			// ---- step 1: unified batch ----
+			// ---- unified batch ----
 			const bool special = (uint32_t)lane < shift;
 			const uint32_t k = (uint32_t)lane - shift;
 			uint32_t pos = special ? anchor - 2u + 2u * lane : p0 + (k ? 1u + accel * (k - 1u) : 0u);
 			const bool en = special || p0 + 1u + accel * k <= mflimit;
 			pos = en ? pos : 0u;                                   // keep disabled lanes' reads in range
-			uint32_t pseq, h;
-			if (WIDE) {
-				const uint64_t v = DIRECT ? read64u(src, pos, lim4)
-				    : ((uint64_t)ring32<RING>(ring, pos) | ((uint64_t)ring32<RING>(ring, pos + 4u) << 32));
-				pseq = (uint32_t)v; h = lz4_hash5(v);
-			} else {
-				pseq = DIRECT ? glob32(src, pos) : ring32<RING>(ring, pos);
-				h = lz4_hash4(pseq);
-			}
-			uint32_t cand = tab.get(h);
+			const Lz4Around ai = lz4_around(src, pos);
+			const uint32_t pseq = ai.at;
+			const uint32_t h = WIDE ? lz4_hash5((uint64_t)ai.at | ((uint64_t)ai.next << 32)) : lz4_hash4(ai.at);
+			const uint32_t cand = tab.get(h);
 			__syncwarp();
 			if (en) tab.put(h, pos);                                // speculative commit
 			__syncwarp();
-			const uint32_t cseq = glob32(src, cand);                // latency overlaps the read-back
-			const bool clash = en && tab.get(h) != (WIDE ? pos : (pos & 0xffffu));
-			const bool hit = en && !(special && lane == 0) && cand + LZ4_FAR >= pos && cseq == pseq;
-			const uint32_t clashes = __ballot_sync(CMB_FULL, clash);
+			const Lz4Around ac = lz4_around(src, cand);             // latency overlaps the read-back
+			const uint32_t seen = tab.get(h);
+			const bool foreign = en && seen != (WIDE ? pos : (pos & 0xffffu));
+			const bool hit = en && !(special && lane == 0) && cand + LZ4_FAR >= pos && ac.at == pseq;
+			const uint32_t foreigns = __ballot_sync(CMB_FULL, foreign);
 			const uint32_t hits = __ballot_sync(CMB_FULL, hit);
-			uint32_t ip, match;
+			// match extension known to this lane: up to 8 bytes forward, 4 backward
+			uint32_t nf, nb;
+			{
+				const uint64_t xf = ((uint64_t)(ai.next ^ ac.next)) | ((uint64_t)(ai.next2 ^ ac.next2) << 32);
+				nf = xf ? (uint32_t)(__ffsll((long long)xf) - 1) >> 3 : 8u;
+				nf = min(nf, mlimit - min(pos + LZ4_MIN_MATCH, mlimit));
+				const uint32_t xb = ai.before ^ ac.before;
+				nb = xb ? (uint32_t)__clz(xb) >> 3 : 4u;
+				nb = min(nb, min(pos - min(anchor, pos), cand));
+				if (special) nb = 0;                               // the re-test starts a sequence as is
+			}
+			// lanes below the lowest lane that met a foreign value form a dependency-free prefix
+			const int t = foreigns ? __ffs(foreigns) - 1 : 32;
+			const int w = hits ? __ffs(hits) - 1 : 32;
+			uint32_t ip, match, fwd, back;
 			bool retest_hit;
-			if (clashes == 0u && hits != 0u) {
-				const int w = __ffs(hits) - 1;
-				if (en && lane > w) tab.put(h, cand);                // undo past the winner
+			if (w < t) {
+				// put the old value back past the winner, unless the slot now holds the position
+				// of a lane at or before the winner (a committed write that must stay)
+				const uint32_t pos_w = __shfl_sync(CMB_FULL, pos, w);
+				if (en && lane > w && !(foreign && seen <= (WIDE ? pos_w : (pos_w & 0xffffu)))) tab.put(h, cand);
 				__syncwarp();
-				ip = __shfl_sync(CMB_FULL, pos, w);
+				ip = pos_w;
 				match = __shfl_sync(CMB_FULL, cand, w);
+				fwd = __shfl_sync(CMB_FULL, nf, w);
+				back = __shfl_sync(CMB_FULL, nb, w);
 				retest_hit = (uint32_t)w < shift;
+				if (fwd == 8u) fwd = 8u + lz4_count_long(src, ip + 12u, match + 12u, mlimit, lim4, lane);
+				if (back == 4u && ip >= anchor + 5u && match >= 5u)
+					back = 4u + lz4_catchup_long(src, ip - 4u, match - 4u, anchor, lane);
 			} else {
 				uint64_t res = 0;
 				const uint32_t enmask = __ballot_sync(CMB_FULL, en);
-				if (clashes) {                                       // two lanes, one slot: redo in order
+				if (t < 32) {
+					// a lane at or before the first hit depends on an earlier lane of the batch:
+					// undo everything and redo the search in program order
 					if (en) tab.put(h, cand);
 					__syncwarp();
 					res = lz4_search_slow<WIDE>(src, lim4, tab, anchor, shift, accel, mflimit, 0, lane);
@@ -337,39 +302,8 @@ __device__ uint32_t lz4_encode_warp(const uint8_t *__restrict__ src, uint32_t n,
 				retest_hit = (res >> 62) & 1u;
 				ip = (uint32_t)(res >> 32) & 0x3fffffffu;
 				match = (uint32_t)res;
-				if (!DIRECT && (ip + LZ4_AHEAD > win.done)) {         // found far ahead: move the window there
-					uint64_t r = lz4_window_refill<RING>(src, ring, n16, win.lo, win.hi, ip, lane);
-					win.lo = (uint32_t)r & 0x1fffffu; win.hi = (uint32_t)(r >> 21) & 0x1fffffu; win.done = (uint32_t)(r >> 42);
-				}
-			}
-
-			// ---- step 2: extend forward (lanes 0-15, lz4.c:415-439) and backward (lanes 16-31,
-			// lz4.c:622) with one instruction stream: lane compares 4 bytes at ip+d against match+d
-			uint32_t fwd, back;
-			{
-				const bool fw = lane < 16;
-				const uint32_t kb = (uint32_t)lane - 15u;                       // backward step of lanes 16..31
-				const uint32_t pa = fw ? ip + LZ4_MIN_MATCH + 4u * lane : ip - kb;
-				const uint32_t pb = fw ? match + LZ4_MIN_MATCH + 4u * lane : match - kb;
-				const bool bw_ok = !fw && !retest_hit && ip >= anchor + kb && match >= kb;
-				const bool deep = bw_ok && !DIRECT && pa < win.lo;               // behind the window: rare
-				const bool live = fw ? pa < mlimit : (bw_ok && !deep);
-				const uint32_t pas = live ? pa : ip, pbs = live ? pb : match;    // keep dead lanes in range
-				const uint32_t x = (DIRECT ? glob32(src, pas) : ring32<RING>(ring, pas)) ^ glob32(src, pbs);
-				uint32_t nf = x ? (uint32_t)(__ffs(x) - 1) >> 3 : 4u;
-				nf = live ? min(nf, fw ? mlimit - pa : 1u) : 0u;
-				const bool flag = fw ? nf < 4u : nf == 0u;
-				const uint32_t bal = __ballot_sync(CMB_FULL, flag);
-				const uint32_t f = bal & 0xffffu, b = bal >> 16;
-				if (f) {
-					const int fl = __ffs(f) - 1;
-					fwd = 4u * fl + __shfl_sync(CMB_FULL, nf, fl);
-				} else {
-					fwd = 64u + lz4_count_long(src, ip + LZ4_MIN_MATCH + 64u, match + LZ4_MIN_MATCH + 64u, mlimit, lim4, lane);
-				}
-				if (__any_sync(CMB_FULL, deep)) back = lz4_catchup_long(src, ip, match, anchor, lane);
-				else if (b) back = (uint32_t)(__ffs(b) - 1);
-				else back = 16u + lz4_catchup_long(src, ip - 16u, match - 16u, anchor, lane);
+				fwd = lz4_count_long(src, ip + LZ4_MIN_MATCH, match + LZ4_MIN_MATCH, mlimit, lim4, lane);
+				back = retest_hit ? 0u : lz4_catchup_long(src, ip, match, anchor, lane);
 			}
 			const uint32_t off = ip - match;
 			const uint32_t mc = back + fwd;               // lz4.c:660 matchCode
@@ -396,7 +330,6 @@ __device__ uint32_t lz4_encode_warp(const uint8_t *__restrict__ src, uint32_t n,
 			if (end > mflimit) break;                     // lz4.c:688
 		}
 	}
-	if (!DIRECT) cp_async_wait<0>();
 
 	// ---- last literals (lz4.c:713-729) ----
 	uint32_t run = n - anchor;
