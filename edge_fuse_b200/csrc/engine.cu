@@ -50,6 +50,10 @@ struct cmb200_engine {
 	int32_t *d_lens = nullptr, *d_status = nullptr;
 	uint64_t *d_fps = nullptr, *d_recoff = nullptr;
 	unsigned int *d_work = nullptr;
+	// page-locked staging for the small per-chunk arrays, so that no copy ever blocks the host
+	// thread that is feeding the pipeline (a pageable cudaMemcpyAsync waits for the stream)
+	static constexpr size_t META_CAP = 1u << 18;   // chunks per outer slice of a call
+	uint8_t *h_meta = nullptr;                     // META_CAP x (16 addr + 8 ts + 4 lens + 4 status + 1 valid)
 	unsigned long long seq = 1;          // sequence of the next chunk
 	unsigned long long seq_stride = 1;   // > 1 when the global stream is sharded round-robin over ranks
 	// per-launch device timing of the dominant kernels (roofline evidence for bench.py)
@@ -99,6 +103,7 @@ extern "C" void cmb200_engine_destroy(cmb200_engine *e) {
 	cudaFree(e->table.slots); cudaFree(e->table.fp); cudaFree(e->arena.base); cudaFree(e->d_counters);
 	cudaFree(e->d_pages[0]); cudaFree(e->d_pages[1]); cudaFree(e->d_stage);
 	cudaFree(e->d_addr); cudaFree(e->d_ts); cudaFree(e->d_valid); cudaFree(e->d_slot); cudaFree(e->d_vlen);
+	if (e->h_meta) cudaFreeHost(e->h_meta);
 	cudaFree(e->d_lens); cudaFree(e->d_status); cudaFree(e->d_fps); cudaFree(e->d_recoff); cudaFree(e->d_work);
 	for (int i = 0; i < 2; i++) {
 		if (e->landed[i]) cudaEventDestroy(e->landed[i]);
@@ -162,16 +167,20 @@ extern "C" cmb200_engine *cmb200_engine_create(const cmb200_config *cfg) {
 		ENG_CHECK(cudaMalloc(&e->d_pages[0], B * e->bsize + 256));
 		ENG_CHECK(cudaMalloc(&e->d_pages[1], B * e->bsize + 256));
 		ENG_CHECK(cudaMalloc(&e->d_stage, B * e->stage_stride + 256));
-		ENG_CHECK(cudaMalloc(&e->d_addr, B * 16));
-		ENG_CHECK(cudaMalloc(&e->d_ts, B * 8));
-		ENG_CHECK(cudaMalloc(&e->d_valid, B));
+		// small per-chunk arrays are sized for a whole slice of a call (META_CAP chunks) so that
+		// they cross PCIe once, outside the page pipeline
+		const uint64_t M = cmb200_engine::META_CAP > B ? cmb200_engine::META_CAP : B;
+		ENG_CHECK(cudaMalloc(&e->d_addr, M * 16));
+		ENG_CHECK(cudaMalloc(&e->d_ts, M * 8));
+		ENG_CHECK(cudaMalloc(&e->d_valid, M));
 		ENG_CHECK(cudaMalloc(&e->d_slot, B * 4));
 		ENG_CHECK(cudaMalloc(&e->d_vlen, B * 4));
-		ENG_CHECK(cudaMalloc(&e->d_lens, B * 4));
-		ENG_CHECK(cudaMalloc(&e->d_status, B * 4));
+		ENG_CHECK(cudaMalloc(&e->d_lens, M * 4));
+		ENG_CHECK(cudaMalloc(&e->d_status, M * 4));
 		ENG_CHECK(cudaMalloc(&e->d_fps, B * 16));
 		ENG_CHECK(cudaMalloc(&e->d_recoff, B * 8));
 		ENG_CHECK(cudaMalloc(&e->d_work, 64));
+		ENG_CHECK(cudaMallocHost(&e->h_meta, cmb200_engine::META_CAP * 33));
 
 		uint64_t arena = cfg->arena_bytes;
 		if (!arena) {
@@ -229,12 +238,27 @@ extern "C" int cmb200_sync(cmb200_engine *e) {
 
 // ---- put ---------------------------------------------------------------------------------
 
-static int put_impl(cmb200_engine *e, size_t n, const cmb200_addr *addr, const uint8_t *valid,
+static int put_slice(cmb200_engine *e, size_t n, const cmb200_addr *addr, const uint8_t *valid,
     const uint8_t *pages, bool pages_on_dev, const uint64_t *ts, int32_t *lens_out) {
-	std::lock_guard<std::mutex> g(e->mu);
-	CMB_CHECK(cudaSetDevice(e->device));
 	const size_t B = e->max_batch;
+	// stage the small arrays in page-locked memory once; every copy below is then truly async
+	cmb200_addr *h_addr = (cmb200_addr *)e->h_meta;
+	uint64_t *h_ts = (uint64_t *)(e->h_meta + cmb200_engine::META_CAP * 16);
+	int32_t *h_lens = (int32_t *)(e->h_meta + cmb200_engine::META_CAP * 24);
+	uint8_t *h_valid = e->h_meta + cmb200_engine::META_CAP * 32;
+	memcpy(h_addr, addr, n * 16);
+	if (ts) memcpy(h_ts, ts, n * 8);
+	if (valid) memcpy(h_valid, valid, n);
+	// The small arrays go over once, before the page pipeline starts: a small copy issued between
+	// two page copies would queue behind the next 256 MiB transfer in the copy engine and stall
+	// the kernels that wait for it.
+	CMB_CHECK(cudaMemcpyAsync(e->d_addr, h_addr, n * 16, cudaMemcpyHostToDevice, e->st));
+	if (valid) CMB_CHECK(cudaMemcpyAsync(e->d_valid, h_valid, n, cudaMemcpyHostToDevice, e->st));
+	if (ts) CMB_CHECK(cudaMemcpyAsync(e->d_ts, h_ts, n * 8, cudaMemcpyHostToDevice, e->st));
 	size_t nb = 0;
+	static const bool trace = getenv("CMB200_TRACE") != nullptr;
+	cudaEvent_t tr[4][16];
+	if (trace) for (int i = 0; i < 4; i++) for (int j = 0; j < 16; j++) cudaEventCreate(&tr[i][j]);
 	for (size_t at = 0; at < n; at += B, nb++) {
 		const uint32_t m = (uint32_t)((n - at < B) ? n - at : B);
 		const int buf = (int)(nb & 1);
@@ -244,41 +268,48 @@ static int put_impl(cmb200_engine *e, size_t n, const cmb200_addr *addr, const u
 		} else {
 			// land the pages in ring buffer `buf` once the kernels that last read it are done
 			CMB_CHECK(cudaStreamWaitEvent(e->copy, e->consumed[buf], 0));
+			if (trace && nb < 16) cudaEventRecord(tr[0][nb], e->copy);
 			CMB_CHECK(cudaMemcpyAsync(e->d_pages[buf], pages + at * e->bsize, (size_t)m * e->bsize,
 			    cudaMemcpyHostToDevice, e->copy));
+			if (trace && nb < 16) cudaEventRecord(tr[1][nb], e->copy);
 			CMB_CHECK(cudaEventRecord(e->landed[buf], e->copy));
 			CMB_CHECK(cudaStreamWaitEvent(e->st, e->landed[buf], 0));
 			d_in = e->d_pages[buf];
 		}
-		// The small per-chunk arrays ride the compute stream; the previous sub-batch's kernels
-		// are ordered before them, so the single set of device arrays is safe to reuse.
-		CMB_CHECK(cudaMemcpyAsync(e->d_addr, addr + at, (size_t)m * 16, cudaMemcpyHostToDevice, e->st));
-		if (valid) CMB_CHECK(cudaMemcpyAsync(e->d_valid, valid + at, m, cudaMemcpyHostToDevice, e->st));
-		if (ts) CMB_CHECK(cudaMemcpyAsync(e->d_ts, ts + at, (size_t)m * 8, cudaMemcpyHostToDevice, e->st));
-		if (launch_upsert(e->table, e->d_addr, valid ? e->d_valid : nullptr, m, e->seq, e->seq_stride, e->d_slot, e->st)) return -1;
+		if (launch_upsert(e->table, e->d_addr + 2 * at, valid ? e->d_valid + at : nullptr, m, e->seq, e->seq_stride, e->d_slot, e->st)) return -1;
 		EncodeJob job{};
 		job.pages = d_in; job.page_stride = e->bsize; job.nbytes = e->bsize; job.n = m;
 		job.accel = (uint32_t)e->accel;
 		job.stage = e->d_stage; job.stage_stride = e->stage_stride;
-		job.lens = e->d_lens;
+		job.lens = e->d_lens + at;
 		job.fps = (e->flags & CMB200_FINGERPRINT) ? e->d_fps : nullptr;
 		job.work = e->d_work;
 		job.slot_idx = e->d_slot;
-		job.addr = e->d_addr;
-		job.ts = ts ? e->d_ts : nullptr;
+		job.addr = e->d_addr + 2 * at;
+		job.ts = ts ? e->d_ts + at : nullptr;
 		job.seq0 = e->seq; job.seq_stride = e->seq_stride;
 		job.table = e->table; job.arena = e->arena;
 		CMB_CHECK(cudaEventRecord(e->t0[nb % e->RING], e->st));
+		if (trace && nb < 16) cudaEventRecord(tr[2][nb], e->st);
 		if (launch_encode(job, e->st)) return -1;
+		if (trace && nb < 16) cudaEventRecord(tr[3][nb], e->st);
 		CMB_CHECK(cudaEventRecord(e->t1[nb % e->RING], e->st));
 		if (!pages_on_dev) CMB_CHECK(cudaEventRecord(e->consumed[buf], e->st));
-		if (lens_out) CMB_CHECK(cudaMemcpyAsync(lens_out + at, e->d_lens, (size_t)m * 4, cudaMemcpyDeviceToHost, e->st));
 		e->seq += (unsigned long long)m * e->seq_stride;
 		e->stats.kernel_launches += 2;
-		// addr/valid/ts host arrays of the NEXT sub-batch are copied with cudaMemcpyAsync from
-		// pageable memory, which returns only after staging: no lifetime issue for the caller.
 	}
+	if (lens_out) CMB_CHECK(cudaMemcpyAsync(h_lens, e->d_lens, n * 4, cudaMemcpyDeviceToHost, e->st));
 	CMB_CHECK(cudaStreamSynchronize(e->st));
+	if (trace) {
+		for (size_t k = 0; k < nb && k < 16 && !pages_on_dev; k++) {
+			float a = 0, b = 0, c = 0, d = 0;
+			cudaEventElapsedTime(&a, tr[0][0], tr[0][k]); cudaEventElapsedTime(&b, tr[0][0], tr[1][k]);
+			cudaEventElapsedTime(&c, tr[0][0], tr[2][k]); cudaEventElapsedTime(&d, tr[0][0], tr[3][k]);
+			fprintf(stderr, "sub-batch %zu: copy %.2f-%.2f ms  encode %.2f-%.2f ms\n", k, a, b, c, d);
+		}
+		for (int i = 0; i < 4; i++) for (int j = 0; j < 16; j++) cudaEventDestroy(tr[i][j]);
+	}
+	if (lens_out) memcpy(lens_out, h_lens, n * 4);
 	for (size_t k = 0; k < nb && k < (size_t)e->RING; k++) {
 		float ms = 0;
 		CMB_CHECK(cudaEventElapsedTime(&ms, e->t0[k], e->t1[k]));
@@ -286,6 +317,18 @@ static int put_impl(cmb200_engine *e, size_t n, const cmb200_addr *addr, const u
 		e->stats.encode_kernel_launches++;
 	}
 	e->stats.put_chunks += n;
+	return 0;
+}
+
+static int put_impl(cmb200_engine *e, size_t n, const cmb200_addr *addr, const uint8_t *valid,
+    const uint8_t *pages, bool pages_on_dev, const uint64_t *ts, int32_t *lens_out) {
+	std::lock_guard<std::mutex> g(e->mu);
+	CMB_CHECK(cudaSetDevice(e->device));
+	for (size_t at = 0; at < n; at += cmb200_engine::META_CAP) {
+		size_t m = n - at < cmb200_engine::META_CAP ? n - at : cmb200_engine::META_CAP;
+		if (put_slice(e, m, addr + at, valid ? valid + at : nullptr, pages + at * e->bsize, pages_on_dev,
+			ts ? ts + at : nullptr, lens_out ? lens_out + at : nullptr)) return -1;
+	}
 	return 0;
 }
 
@@ -300,29 +343,30 @@ extern "C" int cmb200_put_batch_dev(cmb200_engine *e, size_t n, const cmb200_add
 
 // ---- get ---------------------------------------------------------------------------------
 
-static int get_impl(cmb200_engine *e, size_t n, const cmb200_addr *addr, const uint8_t *valid,
-    uint8_t *pages_out, bool out_on_dev, int32_t *status_out, uint64_t *owner_out = nullptr) {
-	std::lock_guard<std::mutex> g(e->mu);
-	CMB_CHECK(cudaSetDevice(e->device));
+static int get_slice(cmb200_engine *e, size_t n, const cmb200_addr *addr, const uint8_t *valid,
+    uint8_t *pages_out, bool out_on_dev, int32_t *status_out) {
 	const size_t B = e->max_batch;
+	cmb200_addr *h_addr = (cmb200_addr *)e->h_meta;
+	int32_t *h_status = (int32_t *)(e->h_meta + cmb200_engine::META_CAP * 28);
+	uint8_t *h_valid = e->h_meta + cmb200_engine::META_CAP * 32;
+	memcpy(h_addr, addr, n * 16);
+	if (valid) memcpy(h_valid, valid, n);
+	CMB_CHECK(cudaMemcpyAsync(e->d_addr, h_addr, n * 16, cudaMemcpyHostToDevice, e->st));
+	if (valid) CMB_CHECK(cudaMemcpyAsync(e->d_valid, h_valid, n, cudaMemcpyHostToDevice, e->st));
 	size_t nb = 0;
 	for (size_t at = 0; at < n; at += B, nb++) {
 		const uint32_t m = (uint32_t)((n - at < B) ? n - at : B);
 		const int buf = (int)(nb & 1);
 		uint8_t *d_out = out_on_dev ? pages_out + at * e->bsize : e->d_pages[buf];
 		if (!out_on_dev) CMB_CHECK(cudaStreamWaitEvent(e->st, e->consumed[buf], 0));   // D2H of buf finished
-		CMB_CHECK(cudaMemcpyAsync(e->d_addr, addr + at, (size_t)m * 16, cudaMemcpyHostToDevice, e->st));
-		if (valid) CMB_CHECK(cudaMemcpyAsync(e->d_valid, valid + at, m, cudaMemcpyHostToDevice, e->st));
-		if (launch_lookup(e->table, e->d_addr, valid ? e->d_valid : nullptr, m, e->d_status, e->d_recoff,
+		if (launch_lookup(e->table, e->d_addr + 2 * at, valid ? e->d_valid + at : nullptr, m, e->d_status + at, e->d_recoff,
 			e->d_vlen, nullptr, e->st)) return -1;
 		DecodeJob job{};
-		job.n = m; job.nbytes = e->bsize; job.pages = d_out; job.status = e->d_status;
+		job.n = m; job.nbytes = e->bsize; job.pages = d_out; job.status = e->d_status + at;
 		job.rec_off = e->d_recoff; job.vlen = e->d_vlen; job.arena = e->arena.base;
 		CMB_CHECK(cudaEventRecord(e->t0[nb % e->RING], e->st));
 		if (launch_decode(job, e->st)) return -1;
 		CMB_CHECK(cudaEventRecord(e->t1[nb % e->RING], e->st));
-		CMB_CHECK(cudaMemcpyAsync(status_out + at, e->d_status, (size_t)m * 4, cudaMemcpyDeviceToHost, e->st));
-		if (owner_out) CMB_CHECK(cudaMemcpyAsync(owner_out + at, e->d_recoff, (size_t)m * 8, cudaMemcpyDeviceToHost, e->st));
 		if (!out_on_dev) {
 			CMB_CHECK(cudaEventRecord(e->landed[buf], e->st));
 			CMB_CHECK(cudaStreamWaitEvent(e->copy, e->landed[buf], 0));
@@ -332,8 +376,10 @@ static int get_impl(cmb200_engine *e, size_t n, const cmb200_addr *addr, const u
 		}
 		e->stats.kernel_launches += 2;
 	}
+	CMB_CHECK(cudaMemcpyAsync(h_status, e->d_status, n * 4, cudaMemcpyDeviceToHost, e->st));
 	CMB_CHECK(cudaStreamSynchronize(e->st));
 	CMB_CHECK(cudaStreamSynchronize(e->copy));
+	memcpy(status_out, h_status, n * 4);
 	for (size_t k = 0; k < nb && k < (size_t)e->RING; k++) {
 		float ms = 0;
 		CMB_CHECK(cudaEventElapsedTime(&ms, e->t0[k], e->t1[k]));
@@ -343,6 +389,18 @@ static int get_impl(cmb200_engine *e, size_t n, const cmb200_addr *addr, const u
 	for (size_t i = 0; i < n; i++) {
 		if (status_out[i] != CMB200_INVALID) e->stats.get_requests++;
 		if (status_out[i] == CMB200_HIT) e->stats.get_hits++;
+	}
+	return 0;
+}
+
+static int get_impl(cmb200_engine *e, size_t n, const cmb200_addr *addr, const uint8_t *valid,
+    uint8_t *pages_out, bool out_on_dev, int32_t *status_out) {
+	std::lock_guard<std::mutex> g(e->mu);
+	CMB_CHECK(cudaSetDevice(e->device));
+	for (size_t at = 0; at < n; at += cmb200_engine::META_CAP) {
+		size_t m = n - at < cmb200_engine::META_CAP ? n - at : cmb200_engine::META_CAP;
+		if (get_slice(e, m, addr + at, valid ? valid + at : nullptr, pages_out + at * e->bsize, out_on_dev,
+			status_out + at)) return -1;
 	}
 	return 0;
 }

@@ -1,2 +1,2 @@
-timeout 600 python -m pytest tests -m gpu -q --timeout 240 -x 2>&1 | tail -3
-timeout 120 python tools/kernel_bench.py --classes RTZMB --chunks 4096 --reps 2 2>&1 | grep -E '^[RTZMB] ' | cut -c1-60
+timeout 600 python -m pytest tests -m gpu -q --timeout 240 2>&1 | tail -2
+timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print({k:d[k] for k in ('value','ms_per_step','e2e')}, d['roofline']['frac'], d['roofline']['avg_launch_ms'])"
