@@ -260,3 +260,23 @@ def test_remote_index_import(E, gpu, oracle):
     assert (status[:5] == E.HIT).all() and status[5] == E.REMOTE
     assert eng.stats()["remote_entries"] == 46 and eng.entries() == 55
     eng.close()
+
+
+def test_c_caller_links_like_edgefs(E, gpu, tmp_path):
+    """A plain C program against include/cachemap.h and -lcachemap (the way edgefs links,
+    Makefile:20,28): async inserts, read-back with byte checks, counters, free."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "drop_in_test"
+    lib_dir = os.path.dirname(E.library_path())
+    subprocess.run(["gcc", "-std=c99", "-D_DEFAULT_SOURCE", "-O2", "-I", os.path.join(root, "include"),
+                    os.path.join(root, "tests", "c", "drop_in_test.c"), "-L", lib_dir, "-lcachemap",
+                    f"-Wl,-rpath,{lib_dir}", "-o", str(exe)], check=True)
+    store = tmp_path / "store"
+    store.mkdir()
+    env = dict(os.environ, CMB200_ARENA_MB="512", CMB200_MAX_BATCH="512")
+    for pshift, n in ((15, 300), (16, 200), (12, 500)):
+        out = subprocess.run([str(exe), str(store), str(pshift), str(n)], capture_output=True, text=True, env=env,
+                             timeout=200)
+        assert out.returncode == 0, (pshift, out.returncode, out.stdout, out.stderr)
+        assert "drop_in_test ok" in out.stdout and "ratio:" in out.stdout
