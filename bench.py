@@ -390,7 +390,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--chunks", type=int, default=16384, help="chunks per GPU per step (16384 = 1 GiB)")
-    ap.add_argument("--max-batch", type=int, default=4096)
+    ap.add_argument("--max-batch", type=int, default=16384, help="chunks per kernel launch (resident pages)")
     ap.add_argument("--cpu-sample-chunks", type=int, default=8192)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

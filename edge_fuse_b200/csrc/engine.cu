@@ -34,7 +34,8 @@ struct cmb200_engine {
 	uint32_t bsize = 65536;
 	int accel = 12;
 	uint64_t capacity = 0;
-	uint32_t max_batch = 4096;
+	uint32_t max_batch = 4096;   // chunks per kernel launch (stage buffer size)
+	uint32_t host_batch = 4096;  // chunks per H2D/D2H pipeline step (page ring size), <= max_batch
 	uint32_t flags = 0;
 	cudaStream_t st = nullptr, copy = nullptr;
 	cudaEvent_t landed[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr};
@@ -129,6 +130,13 @@ extern "C" cmb200_engine *cmb200_engine_create(const cmb200_config *cfg) {
 	e->accel = cfg->accel < 0 ? 1 : (cfg->accel > (1 << 20) ? (1 << 20) : cfg->accel);   // lz4.c:740
 	e->capacity = cfg->capacity;
 	e->max_batch = cfg->max_batch ? cfg->max_batch : 4096;
+	{
+		// host pages are pipelined in smaller steps than a resident batch is launched in: the first
+		// copy of a call cannot overlap anything, while a launch wants many chunks per warp
+		const char *hb = getenv("CMB200_HOST_BATCH");
+		uint32_t v = hb ? (uint32_t)strtoul(hb, nullptr, 0) : 4096u;
+		e->host_batch = v && v < e->max_batch ? v : e->max_batch;
+	}
 	e->flags = cfg->flags;
 	const uint64_t B = e->max_batch;
 	{
@@ -164,8 +172,8 @@ extern "C" cmb200_engine *cmb200_engine_create(const cmb200_config *cfg) {
 		e->table.remote = e->d_counters + 5;
 
 		e->stage_stride = ((uint64_t)e->bsize + 1024 + 15) & ~15ull;        // filemap.c:120 dest[bsize+1024]
-		ENG_CHECK(cudaMalloc(&e->d_pages[0], B * e->bsize + 256));
-		ENG_CHECK(cudaMalloc(&e->d_pages[1], B * e->bsize + 256));
+		ENG_CHECK(cudaMalloc(&e->d_pages[0], (uint64_t)e->host_batch * e->bsize + 256));
+		ENG_CHECK(cudaMalloc(&e->d_pages[1], (uint64_t)e->host_batch * e->bsize + 256));
 		ENG_CHECK(cudaMalloc(&e->d_stage, B * e->stage_stride + 256));
 		// small per-chunk arrays are sized for a whole slice of a call (META_CAP chunks) so that
 		// they cross PCIe once, outside the page pipeline
@@ -240,7 +248,7 @@ extern "C" int cmb200_sync(cmb200_engine *e) {
 
 static int put_slice(cmb200_engine *e, size_t n, const cmb200_addr *addr, const uint8_t *valid,
     const uint8_t *pages, bool pages_on_dev, const uint64_t *ts, int32_t *lens_out) {
-	const size_t B = e->max_batch;
+	const size_t B = pages_on_dev ? e->max_batch : e->host_batch;
 	// stage the small arrays in page-locked memory once; every copy below is then truly async
 	cmb200_addr *h_addr = (cmb200_addr *)e->h_meta;
 	uint64_t *h_ts = (uint64_t *)(e->h_meta + cmb200_engine::META_CAP * 16);
@@ -345,7 +353,7 @@ extern "C" int cmb200_put_batch_dev(cmb200_engine *e, size_t n, const cmb200_add
 
 static int get_slice(cmb200_engine *e, size_t n, const cmb200_addr *addr, const uint8_t *valid,
     uint8_t *pages_out, bool out_on_dev, int32_t *status_out) {
-	const size_t B = e->max_batch;
+	const size_t B = out_on_dev ? e->max_batch : e->host_batch;
 	cmb200_addr *h_addr = (cmb200_addr *)e->h_meta;
 	int32_t *h_status = (int32_t *)(e->h_meta + cmb200_engine::META_CAP * 28);
 	uint8_t *h_valid = e->h_meta + cmb200_engine::META_CAP * 32;

@@ -39,7 +39,8 @@ typedef struct cmb200_config {
 	uint64_t capacity;      /* entries before eviction starts (cachemap_create capacity) */
 	uint64_t arena_bytes;   /* HBM arena for records, 0 = sized from capacity and free memory */
 	uint64_t table_slots;   /* key-table slots (power of two), 0 = 4 x capacity rounded up */
-	uint32_t max_batch;     /* chunks per device batch, 0 = 4096 */
+	uint32_t max_batch;     /* chunks per kernel launch, 0 = 4096 (host pages are pipelined in
+	                         * steps of min(max_batch, CMB200_HOST_BATCH = 4096) chunks) */
 	uint32_t flags;
 } cmb200_config;
 
