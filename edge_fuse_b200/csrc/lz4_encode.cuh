@@ -26,8 +26,8 @@
 //         first hit (ballot) lies there it wins and the later lanes put the old values back.
 //         Otherwise (a true intra-batch dependency, or 30 probes were not enough) the general
 //         search lz4_search_slow resolves program order with __match_any_sync.
-//       Each lane fetches 16 bytes around its probe and around its candidate in that same round
-//         trip, so the winner already knows the match extension up to 8 bytes forward
+//       Each lane fetches 12 bytes around its probe and around its candidate in that same round
+//         trip, so the winner already knows the match extension up to 4 bytes forward
 //         (lz4.c:415-439) and 4 bytes backward (lz4.c:622); longer ones go out of line.
 //   * The hot loop is kept small on purpose (the profile of the first version showed a third of
 //     the stall samples waiting on instruction fetch): rare paths are __noinline__.
@@ -68,20 +68,19 @@ template <> struct Lz4Table<true> {
 	__device__ __forceinline__ void put(uint32_t h, uint32_t pos) const { t[h] = pos; }
 };
 
-// The 16 bytes [p-4, p+12) of the page as four little-endian words {before, at, next, next2}.
-// Five aligned loads (page buffers are padded past their end; the word before the page start is
-// never needed because backward extension is capped by the position itself).
-struct Lz4Around { uint32_t before, at, next, next2; };
+// The 12 bytes [p-4, p+8) of the page as three little-endian words {before, at, next}: four
+// aligned loads (page buffers are padded past their end; the word before the page start is never
+// needed because backward extension is capped by the position itself).
+struct Lz4Around { uint32_t before, at, next; };
 __device__ __forceinline__ Lz4Around lz4_around(const uint8_t *src, uint32_t p) {
 	const uint32_t a = p & ~3u, sh = (p & 3u) * 8u;
 	const uint32_t *q = reinterpret_cast<const uint32_t *>(src + a);
 	const uint32_t w0 = a ? __ldg(q - 1) : 0u;
-	const uint32_t w1 = __ldg(q), w2 = __ldg(q + 1), w3 = __ldg(q + 2), w4 = __ldg(q + 3);
+	const uint32_t w1 = __ldg(q), w2 = __ldg(q + 1), w3 = __ldg(q + 2);
 	Lz4Around r;
 	r.before = __funnelshift_r(w0, w1, sh);
 	r.at = __funnelshift_r(w1, w2, sh);
 	r.next = __funnelshift_r(w2, w3, sh);
-	r.next2 = __funnelshift_r(w3, w4, sh);
 	return r;
 }
 
@@ -256,11 +255,11 @@ __device__ uint32_t lz4_encode_warp(const uint8_t *__restrict__ src, uint32_t n,
 			const bool hit = en && !(special && lane == 0) && cand + LZ4_FAR >= pos && ac.at == pseq;
 			const uint32_t foreigns = __ballot_sync(CMB_FULL, foreign);
 			const uint32_t hits = __ballot_sync(CMB_FULL, hit);
-			// match extension known to this lane: up to 8 bytes forward, 4 backward
+			// match extension known to this lane: up to 4 bytes forward, 4 backward
 			uint32_t nf, nb;
 			{
-				const uint64_t xf = ((uint64_t)(ai.next ^ ac.next)) | ((uint64_t)(ai.next2 ^ ac.next2) << 32);
-				nf = xf ? (uint32_t)(__ffsll((long long)xf) - 1) >> 3 : 8u;
+				const uint32_t xf = ai.next ^ ac.next;
+				nf = xf ? (uint32_t)(__ffs(xf) - 1) >> 3 : 4u;
 				nf = min(nf, mlimit - min(pos + LZ4_MIN_MATCH, mlimit));
 				const uint32_t xb = ai.before ^ ac.before;
 				nb = xb ? (uint32_t)__clz(xb) >> 3 : 4u;
@@ -283,7 +282,7 @@ __device__ uint32_t lz4_encode_warp(const uint8_t *__restrict__ src, uint32_t n,
 				fwd = __shfl_sync(CMB_FULL, nf, w);
 				back = __shfl_sync(CMB_FULL, nb, w);
 				retest_hit = (uint32_t)w < shift;
-				if (fwd == 8u) fwd = 8u + lz4_count_long(src, ip + 12u, match + 12u, mlimit, lim4, lane);
+				if (fwd == 4u) fwd = 4u + lz4_count_long(src, ip + 8u, match + 8u, mlimit, lim4, lane);
 				if (back == 4u && ip >= anchor + 5u && match >= 5u)
 					back = 4u + lz4_catchup_long(src, ip - 4u, match - 4u, anchor, lane);
 			} else {
@@ -315,12 +314,15 @@ __device__ uint32_t lz4_encode_warp(const uint8_t *__restrict__ src, uint32_t n,
 				uint8_t *o = dst + op;
 				const uint32_t hl = 1u + (lit >= 15u);
 				const uint32_t mext = mc >= 15u;
-				if (lane == 0) o[0] = (uint8_t)((min(lit, 15u) << 4) | min(mc, 15u));
-				if (lane == 1 && lit >= 15u) o[1] = (uint8_t)(lit - 15u);
 				if ((uint32_t)lane < lit) o[hl + lane] = (uint8_t)litbyte;
-				if (lane == 31) { o[hl + lit] = (uint8_t)off; o[hl + lit + 1] = (uint8_t)(off >> 8); }
-				if (lane == 30 && mext) o[hl + lit + 2] = (uint8_t)(mc - 15u);
-				op += hl + lit + 2u + mext;
+				// lanes 0-4 each own one of the bytes around the literals
+				const uint32_t tail = hl + lit;
+				const uint32_t at = lane == 0 ? 0u : lane == 1 ? 1u : tail + (uint32_t)lane - 2u;
+				const uint32_t val = lane == 0 ? ((min(lit, 15u) << 4) | min(mc, 15u)) : lane == 1 ? lit - 15u
+				    : lane == 2 ? off : lane == 3 ? off >> 8 : mc - 15u;
+				const bool own = lane == 0 || (lane == 1 && lit >= 15u) || lane == 2 || lane == 3 || (lane == 4 && mext);
+				if (own) o[at] = (uint8_t)val;
+				op += tail + 2u + mext;
 			} else {
 				op = lz4_emit_general(dst, op, src, anchor, lit, off, mc, lane);
 			}
