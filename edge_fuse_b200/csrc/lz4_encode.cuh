@@ -230,18 +230,30 @@ __device__ uint32_t lz4_encode_warp(const uint8_t *__restrict__ src, uint32_t n,
 		const uint32_t mflimit = n - LZ4_MATCH_FIND_MARGIN;
 		const uint32_t mlimit = n - LZ4_TAIL_LITERALS;
 		// lz4.c:583 stores position 0 under hash(0): a no-op on the cleared table, so skipped.
-		uint32_t shift = 0;          // 2 once a match has ended: lanes 0,1 replay lz4.c:691-707
+		// Per-lane constants of the batch that follows a match ending at `end` (lz4.c:691-710):
+		// lane 0 refills end-2, lane 1 re-tests end, lane j >= 2 is probe k = j-2 of the search
+		// starting at end+1, which runs only while the probe after it stays <= mflimit.
+		const uint32_t kk = (uint32_t)lane - 2u;
+		const int32_t delta2 = lane < 2 ? 2 * lane - 2 : (int32_t)(1u + (kk ? 1u + accel * (kk - 1u) : 0u));
+		const uint32_t need2 = lane < 2 ? 0u : 2u + accel * kk;            // end + need2 <= mflimit
+		// first batch of the chunk: plain search from position 1 (lz4.c:584), no refill / re-test
+		uint32_t shift = 0;          // 2 once a match has ended
 		for (;;) {
-			const uint32_t p0 = anchor + 1;       // first probe of the search (lz4.c:584,710)
+			const bool special = (uint32_t)lane < shift;
+			uint32_t pos;
+			bool en;
+			if (shift) {
+				pos = anchor + (uint32_t)delta2;
+				en = anchor + need2 <= mflimit;
+			} else {
+				pos = 1u + (lane ? 1u + accel * ((uint32_t)lane - 1u) : 0u);
+				en = 2u + accel * (uint32_t)lane <= mflimit;
+			}
+			pos = en ? pos : 0u;                                   // keep disabled lanes' reads in range
 			// speculative literal byte: src[anchor + lane] (used when the run is <= 32 bytes)
 			const uint32_t litbyte = ldg8(src + min(anchor + lane, n - 1u));
 
 			// ---- unified batch ----
-			const bool special = (uint32_t)lane < shift;
-			const uint32_t k = (uint32_t)lane - shift;
-			uint32_t pos = special ? anchor - 2u + 2u * lane : p0 + (k ? 1u + accel * (k - 1u) : 0u);
-			const bool en = special || p0 + 1u + accel * k <= mflimit;
-			pos = en ? pos : 0u;                                   // keep disabled lanes' reads in range
 			const Lz4Around ai = lz4_around(src, pos);
 			const uint32_t pseq = ai.at;
 			const uint32_t h = WIDE ? lz4_hash5((uint64_t)ai.at | ((uint64_t)ai.next << 32)) : lz4_hash4(ai.at);
@@ -267,11 +279,12 @@ __device__ uint32_t lz4_encode_warp(const uint8_t *__restrict__ src, uint32_t n,
 				if (special) nb = 0;                               // the re-test starts a sequence as is
 			}
 			// lanes below the lowest lane that met a foreign value form a dependency-free prefix
-			const int t = foreigns ? __ffs(foreigns) - 1 : 32;
-			const int w = hits ? __ffs(hits) - 1 : 32;
+			// (first hit below first foreign lane <=> lowest set bit of `hits` below that of `foreigns`)
+			const uint32_t low_hit = hits & (0u - hits), low_for = foreigns & (0u - foreigns);
 			uint32_t ip, match, fwd, back;
 			bool retest_hit;
-			if (w < t) {
+			if (hits != 0u && (foreigns == 0u || low_hit < low_for)) {
+				const int w = __ffs(hits) - 1;
 				// put the old value back past the winner, unless the slot now holds the position
 				// of a lane at or before the winner (a committed write that must stay)
 				const uint32_t pos_w = __shfl_sync(CMB_FULL, pos, w);
@@ -288,7 +301,7 @@ __device__ uint32_t lz4_encode_warp(const uint8_t *__restrict__ src, uint32_t n,
 			} else {
 				uint64_t res = 0;
 				const uint32_t enmask = __ballot_sync(CMB_FULL, en);
-				if (t < 32) {
+				if (foreigns) {
 					// a lane at or before the first hit depends on an earlier lane of the batch:
 					// undo everything and redo the search in program order
 					if (en) tab.put(h, cand);
