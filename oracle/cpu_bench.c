@@ -119,6 +119,7 @@ ef_cpu_bench_codec(enc_fn enc, dec_fn dec, const uint8_t *data, size_t nchunks, 
 	int stride = bsize + 1024;
 	uint8_t *blocks = malloc(nchunks * (size_t)stride);
 	int *lens = calloc(nchunks, sizeof(int));
+	memset(blocks, 0, nchunks * (size_t)stride);    /* fault the pages in before the clock starts */
 	struct job p;
 	uint64_t bad = 0;
 	memset(&p, 0, sizeof(p));
