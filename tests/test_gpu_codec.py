@@ -134,3 +134,63 @@ def test_fingerprint_matches_spec(E, gpu, oracle):
     _, fps = E.lz4_encode_batch(np.stack(pages), accel=12, fingerprints=True)
     for p, f in zip(pages, fps):
         assert (int(f[0]), int(f[1])) == oracle.fingerprint128(p)
+
+
+def test_encode_fuzz_high_clash(E, gpu, oracle):
+    """Many small pages built to stress the speculative batch: tiny alphabets and short periods
+    (many lanes hashing to one table slot), matches at every distance, runs ending at every
+    offset near the block end.  4-16 KiB so the oracle does 3000 pages in seconds."""
+    pages_by_n = {}
+    idx = 0
+    for n in (4096, 8192, 16384):
+        ps = []
+        for i in range(1000 if n == 4096 else 500):
+            w = datagen.words(777 + idx, 8)
+            mode = int(w[0] % np.uint64(6))
+            if mode == 0:      # alphabet of 2-4 symbols
+                p = (datagen.rand_bytes(idx, n) % np.uint8(2 + int(w[1] % np.uint64(3)))).astype(np.uint8)
+            elif mode == 1:    # period 1..64 with a few flipped bytes
+                per = 1 + int(w[1] % np.uint64(64))
+                p = np.tile(datagen.rand_bytes(idx, per), n // per + 1)[:n].copy()
+                k = int(w[2] % np.uint64(12))
+                if k:
+                    p[(datagen.words(idx ^ 5, k) % np.uint64(n)).astype(np.int64)] ^= 0x55
+            elif mode == 2:    # text-like with runs of zeros
+                p = datagen.make_page("T", n, idx)
+                a = int(w[1] % np.uint64(n - 600)); p[a:a + int(w[2] % np.uint64(600))] = 0
+            elif mode == 3:    # copy of an earlier window at a random distance
+                p = datagen.make_page("R", n, idx)
+                d = 1 + int(w[1] % np.uint64(n // 2)); L = int(w[2] % np.uint64(n // 4))
+                p[d + 100:d + 100 + L] = p[100:100 + L][: max(0, min(L, n - d - 100))]
+            elif mode == 4:    # random bytes with the tail being a repeat (match runs into the end margin)
+                p = datagen.make_page("R", n, idx)
+                t = 5 + int(w[1] % np.uint64(40)); p[n - t:] = p[n - 2 * t:n - t]
+            else:
+                p = datagen.make_page("X", n, idx)
+            ps.append(p)
+            idx += 1
+        pages_by_n[n] = ps
+    for n, ps in pages_by_n.items():
+        for accel in (12, 1):
+            blocks, _ = E.lz4_encode_batch(np.stack(ps), accel=accel)
+            bad = [i for i, (p, b) in enumerate(zip(ps, blocks)) if b != oracle.lz4_encode(p, accel)]
+            assert not bad, (n, accel, bad[:5])
+
+
+def test_encode_wide_mode_fuzz(E, gpu, oracle):
+    """pshift 17 (byU32 table, 12-bit hash5, MAX_DISTANCE test): far matches beyond 64 KiB must be
+    rejected, near ones taken."""
+    n = 131072
+    ps = []
+    for i in range(48):
+        w = datagen.words(4242 + i, 4)
+        p = datagen.make_page("RTXM"[i % 4], n, 9100 + i)
+        d = 60000 + int(w[0] % np.uint64(12000))          # straddles the 65535 limit
+        L = 200 + int(w[1] % np.uint64(3000))
+        p[d + 500:d + 500 + L] = p[500:500 + L]
+        ps.append(p)
+    blocks, _ = E.lz4_encode_batch(np.stack(ps), accel=12)
+    for i, (p, b) in enumerate(zip(ps, blocks)):
+        assert b == oracle.lz4_encode(p, 12), i
+    out, used = E.lz4_decode_batch(blocks, n)
+    assert (used == np.array([len(b) for b in blocks])).all() and (out == np.stack(ps)).all()
