@@ -30,7 +30,7 @@ EXPORTED_SYMBOLS = [
     "cmb200_unset_batch", "cmb200_entries", "cmb200_sample", "cmb200_read_records",
     "cmb200_read_fingerprints", "cmb200_get_stats", "cmb200_compose_keys",
     "cmb200_set_stream_order", "cmb200_import_remote", "cmb200_locate_batch",
-    "cmb200_lz4_encode_batch", "cmb200_lz4_decode_batch", "cmb200_fingerprint_batch",
+    "cmb200_lz4_encode_batch", "cmb200_lz4_decode_batch", "cmb200_fingerprint_batch", "cmb200_fingerprint_dev",
     "cmb200_gen_chunk_host", "cmb200_gen_chunks_dev", "cmb200_gen_stream_ids", "cmb200_gen_addr",
 ]
 
@@ -45,7 +45,8 @@ class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "entries", "table_slots", "tombstones", "arena_bytes", "arena_used", "arena_garbage",
         "dropped_puts", "remote_entries", "put_chunks", "get_requests", "get_hits", "kernel_launches",
-        "encode_kernel_ns", "encode_kernel_launches", "decode_kernel_ns", "decode_kernel_launches")]
+        "encode_kernel_ns", "encode_kernel_launches", "decode_kernel_ns", "decode_kernel_launches",
+        "fingerprint_kernel_ns")]
 
 
 def library_path() -> str:
@@ -113,6 +114,7 @@ def lib() -> C.CDLL:
         "cmb200_lz4_encode_batch": (i32, [i32, vp, sz, u32, sz, i32, vp, sz, vp, vp]),
         "cmb200_lz4_decode_batch": (i32, [i32, vp, sz, vp, sz, u32, vp, vp]),
         "cmb200_fingerprint_batch": (i32, [i32, vp, sz, u32, sz, vp]),
+        "cmb200_fingerprint_dev": (i32, [vp, sz, vp, vp]),
         "cmb200_gen_chunk_host": (None, [u64, u64, u32, vp]),
         "cmb200_gen_chunks_dev": (i32, [vp, u64, vp, sz, vp]),
         "cmb200_gen_stream_ids": (u64, [u64, sz, C.c_double, u64, vp]),
@@ -334,6 +336,11 @@ class Engine:
         _check(lib().cmb200_locate_batch(self.h, len(addr), _ptr(addr), _ptr(status), _ptr(owner)),
                "cmb200_locate_batch")
         return status, owner
+
+    def fingerprint_dev(self, n: int, pages_dev: int) -> np.ndarray:
+        fps = np.zeros((n, 2), dtype=np.uint64)
+        _check(lib().cmb200_fingerprint_dev(self.h, n, pages_dev, _ptr(fps)), "cmb200_fingerprint_dev")
+        return fps
 
     def stats(self) -> dict:
         s = Stats()

@@ -268,6 +268,8 @@ static int put_slice(cmb200_engine *e, size_t n, const cmb200_addr *addr, const 
 	cudaEvent_t tr[4][16];
 	if (trace) for (int i = 0; i < 4; i++) for (int j = 0; j < 16; j++) cudaEventCreate(&tr[i][j]);
 	for (size_t at = 0; at < n; at += B, nb++) {
+		// (splitting the last step into smaller ones to shorten the un-overlapped tail was tried:
+		// launches below ~4096 chunks run below PCIe rate, so the tail got longer, not shorter)
 		const uint32_t m = (uint32_t)((n - at < B) ? n - at : B);
 		const int buf = (int)(nb & 1);
 		const uint8_t *d_in;
@@ -647,6 +649,25 @@ extern "C" int cmb200_fingerprint_batch(int device, const void *pages_host, size
 	CMB_CHECK(cudaMemcpy(d_in.p, pages_host, n * stride, cudaMemcpyHostToDevice));
 	if (launch_fingerprint(d_in.as<uint8_t>(), stride, nbytes, (uint32_t)n, d_fps.as<uint64_t>(), 0)) return -1;
 	CMB_CHECK(cudaMemcpy(fp_out, d_fps.p, n * 16, cudaMemcpyDeviceToHost));
+	return 0;
+}
+
+// EF128 of n resident pages (stand-alone form of the pass that k_encode fuses); the kernel's
+// CUDA-event time is added to stats.fingerprint_kernel_ns.
+extern "C" int cmb200_fingerprint_dev(cmb200_engine *e, size_t n, const void *pages_dev, uint64_t *fp_out_host) {
+	std::lock_guard<std::mutex> g(e->mu);
+	CMB_CHECK(cudaSetDevice(e->device));
+	DevBuf d_fps;
+	if (d_fps.alloc(n * 16)) return -1;
+	CMB_CHECK(cudaEventRecord(e->t0[0], e->st));
+	if (launch_fingerprint((const uint8_t *)pages_dev, e->bsize, e->bsize, (uint32_t)n, d_fps.as<uint64_t>(), e->st)) return -1;
+	CMB_CHECK(cudaEventRecord(e->t1[0], e->st));
+	CMB_CHECK(cudaMemcpyAsync(fp_out_host, d_fps.p, n * 16, cudaMemcpyDeviceToHost, e->st));
+	CMB_CHECK(cudaStreamSynchronize(e->st));
+	float ms = 0;
+	CMB_CHECK(cudaEventElapsedTime(&ms, e->t0[0], e->t1[0]));
+	e->stats.fingerprint_kernel_ns += (uint64_t)(ms * 1e6);
+	e->stats.kernel_launches++;
 	return 0;
 }
 

@@ -108,6 +108,7 @@ typedef struct cmb200_stats {
 	uint64_t put_chunks, get_requests, get_hits, kernel_launches;
 	/* summed CUDA-event durations of the encode / decode kernel launches (last 64 per call) */
 	uint64_t encode_kernel_ns, encode_kernel_launches, decode_kernel_ns, decode_kernel_launches;
+	uint64_t fingerprint_kernel_ns;
 } cmb200_stats;
 int cmb200_get_stats(cmb200_engine *e, cmb200_stats *out);
 
@@ -142,6 +143,8 @@ int cmb200_lz4_decode_batch(int device, const void *blocks_host, size_t in_strid
     size_t n, uint32_t nbytes, void *pages_out_host, int32_t *consumed_out);
 int cmb200_fingerprint_batch(int device, const void *pages_host, size_t n, uint32_t nbytes,
     size_t stride, uint64_t *fp_out);
+/* EF128 of n pages resident in the engine's HBM (1<<pshift bytes each); fp_out on the host. */
+int cmb200_fingerprint_dev(cmb200_engine *e, size_t n, const void *pages_dev, uint64_t *fp_out_host);
 
 /* ---- synthetic streams, same definition on host and device ---- */
 void cmb200_gen_chunk_host(uint64_t seed, uint64_t cid, uint32_t bsize, void *out);

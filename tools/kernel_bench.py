@@ -52,12 +52,16 @@ def main():
             if r:
                 best_e = min(best_e, (s1["encode_kernel_ns"] - s0["encode_kernel_ns"]) * 1e-9)
                 best_d = min(best_d, (s2["decode_kernel_ns"] - s1["decode_kernel_ns"]) * 1e-9)
+        f0 = eng.stats()["fingerprint_kernel_ns"]
+        eng.fingerprint_dev(n, d)
+        eng.fingerprint_dev(n, d)
+        fp_s = (eng.stats()["fingerprint_kernel_ns"] - f0) * 0.5e-9
         stored = float(lens.sum())
         res[cls] = {"encode_gibs": n * bs / 2**30 / best_e, "decode_gibs": n * bs / 2**30 / best_d,
                     "ratio": stored / (n * bs),
                     "encode_alg_gbs": (n * (bs + 88) + stored) / best_e / 1e9,
                     "decode_alg_gbs": (n * (bs + 56) + stored) / best_d / 1e9,
-                    "encode_us_per_chunk_per_warp": None}
+                    "fingerprint_gbs": n * (bs + 16) / fp_s / 1e9}
         print(cls, json.dumps(res[cls]), flush=True)
     eng.close()
 
