@@ -61,6 +61,7 @@ struct EncodeJob {
 	int32_t *lens;           // out: block length, -1 = chunk skipped (superseded inside the batch)
 	uint64_t *fps;           // out, optional: 2 x u64 per chunk {hi, lo}
 	unsigned int *work;      // dynamic work counter (zeroed by the launcher)
+	uint8_t *gtab;           // group encoder: global position tables, set by the launcher
 	// store mode (all null/0 for codec-only use)
 	const uint32_t *slot_idx; // per chunk, from the upsert kernel; 0xffffffff = invalid address
 	const unsigned long long *addr; // per chunk {u,l}

@@ -194,3 +194,42 @@ def test_encode_wide_mode_fuzz(E, gpu, oracle):
         assert b == oracle.lz4_encode(p, 12), i
     out, used = E.lz4_decode_batch(blocks, n)
     assert (used == np.array([len(b) for b in blocks])).all() and (out == np.stack(ps)).all()
+
+
+def test_group_encoder_mode_parity(gpu):
+    """The alternative encoder organisation (CMB200_ENC_MODE=1: 8 lanes per chunk, position tables
+    in global memory) must emit the same bytes; the mode is read once per process, so it runs in
+    a child process over the golden vectors and a slice of the fuzz set."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, os, json, hashlib
+sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
+import numpy as np, datagen, edge_fuse_b200 as E
+from oracle import ef_oracle as O
+g = json.load(open("tests/golden/lz4_blocks.json"))["cases"]
+groups = {}
+for r in g:
+    if r["n"]: groups.setdefault((r["n"], r["accel"]), []).append(r)
+for (n, accel), recs in groups.items():
+    pages = [datagen.make_page(r["kind"], n, r["seed"]) for r in recs]
+    blocks, fps = E.lz4_encode_batch(datagen.pad_rows(pages), nbytes=n, accel=accel, fingerprints=True)
+    for r, p, b, f in zip(recs, pages, blocks, fps):
+        assert hashlib.sha256(b).hexdigest() == r["sha256"], (r["kind"], n, accel)
+        assert (int(f[0]), int(f[1])) == O.fingerprint128(p)
+ps = [datagen.make_page("XTPA"[i % 4], 8192, 31 * i) for i in range(600)]
+blocks, _ = E.lz4_encode_batch(np.stack(ps), accel=12)
+assert all(b == O.lz4_encode(p, 12) for p, b in zip(ps, blocks))
+eng = E.Engine(pshift=16, accel=12, capacity=2048, arena_bytes=128 << 20, max_batch=256, flags=E.FINGERPRINT)
+pages = np.stack([E.gen_chunk_host(42, c, 65536) for c in range(64)])
+u = np.full(64, 3, dtype=np.uint64); l = np.arange(64, dtype=np.uint64)
+eng.put(u, l, pages); out, st = eng.get(u, l)
+assert (st == E.HIT).all() and (out == pages).all()
+fps, ok = eng.read_fingerprints(u, l)
+assert ok.all() and (int(fps[5, 0]), int(fps[5, 1])) == O.fingerprint128(pages[5])
+print("group-mode parity ok")
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, CMB200_ENC_MODE="1"),
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "group-mode parity ok" in out.stdout, out.stdout + out.stderr
