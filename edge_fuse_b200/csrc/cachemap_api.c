@@ -4,15 +4,19 @@
  *
  * What each reference function became:
  *   filemap_create/free        cachemap/filemap.c:35-110   -> config only; engine built lazily
- *   filemap_set/get/unset      cachemap/filemap.c:112-262  -> one request in a combining queue;
- *                              whichever caller finds no batch in flight becomes the leader, takes
- *                              every queued request (each from a different thread, all
- *                              outstanding at once, so any order is a valid linearisation) and
- *                              runs them as one GPU batch: unsets, then sets, then gets
- *   filemap_get_rand/entries   cachemap/filemap.c:264-330  -> table sample kernel / device counter
+ *   filemap_set                cachemap/filemap.c:112-158  -> WRITE-BEHIND: the page is copied into a
+ *                              page-locked ring and the call returns; one flusher thread hands the
+ *                              ring to the GPU in batches.  A single chunk takes the GPU 0.2-3 ms
+ *                              to encode (the LZ4 parse is serial), which no caller should wait
+ *                              for; what the reference guarantees to its callers — a get after a
+ *                              put returns that page — is kept by looking in the ring first.
+ *   filemap_get                cachemap/filemap.c:217-262  -> ring hit, else one request in a
+ *                              combining queue: whichever caller finds no batch in flight becomes
+ *                              the leader and runs every queued request as one GPU batch
+ *   filemap_unset/get_rand/entries  filemap.c:188-330     -> drain the ring, then engine calls
  *   cachemap_*                 cachemap/cachemap.c:107-239 -> same logic: address composition,
- *                              timestamps, evict-min-of-3 when entries >= capacity, counters,
- *                              async queue (one flusher thread that batches instead of 4 workers)
+ *                              timestamps, counters; evict-oldest-of-3 runs in the flusher before
+ *                              each batch; put_async == put (both are write-behind now)
  * There is no CPU fallback: if the engine cannot be created the process stops with a message
  * (set CMB200_SOFT_FAIL=1 to degrade to "every put dropped, every get a miss" instead).
  */
@@ -27,20 +31,26 @@
 #include "../../include/cachemap.h"
 #include "../../include/cachemap_b200.h"
 
-#define COMBINE_MAX 256         /* requests one leader takes per GPU batch */
+#define COMBINE_MAX 256         /* get/unset requests one leader takes per GPU batch */
+#define FLUSH_MAX 1024          /* pages the flusher hands over per GPU batch */
 #define PNUM_SHIFT 44           /* cachemap.c:155 */
 
-enum req_kind { REQ_SET, REQ_GET, REQ_UNSET };
+enum req_kind { REQ_GET, REQ_UNSET };
+enum wb_state { WB_FREE = 0, WB_FILLING, WB_READY, WB_FLUSHING };
 
 struct fm_req {
 	enum req_kind kind;
 	cmb200_addr addr;
-	const void *page;       /* REQ_SET */
-	uint64_t ts;
 	void *out;              /* REQ_GET: malloc()ed page or NULL */
 	int bad_entry;
 	int done;
 	struct fm_req *next;
+};
+
+struct wb_slot {
+	cmb200_addr addr;
+	uint64_t ts;
+	int state;
 };
 
 struct filemap {
@@ -49,16 +59,25 @@ struct filemap {
 	int bsize;
 	int pshift;
 	char destdir[2048];
+	uint64_t capacity;      /* eviction threshold (set by cachemap_create), 0 = none */
 	/* engine, built on first use (fork safety) */
 	pthread_mutex_t init_mu;
 	int init_state;         /* 0 = not yet, 1 = ready, -1 = failed */
 	cmb200_engine *eng;
-	uint8_t *h_stage;       /* page-locked, COMBINE_MAX pages */
-	/* combining queue */
+	uint8_t *h_stage;       /* page-locked, COMBINE_MAX pages (get results) */
+	/* combining queue (gets, unsets) */
 	pthread_mutex_t q_mu;
 	pthread_cond_t q_cv;
 	struct fm_req *q_head, *q_tail;
 	int leader_active;
+	/* write-behind ring: slots [wb_tail, wb_head) are in use, numbered modulo wb_n */
+	pthread_mutex_t wb_mu;
+	pthread_cond_t wb_space, wb_work, wb_idle;
+	uint8_t *wb_pages;      /* page-locked, wb_n pages */
+	struct wb_slot *wb_slot;
+	uint64_t wb_n, wb_head, wb_tail;
+	pthread_t wb_thread;
+	int wb_started, wb_stop;
 };
 
 static long
@@ -67,6 +86,8 @@ env_long(const char *name, long dflt)
 	const char *v = getenv(name);
 	return (v && *v) ? strtol(v, NULL, 0) : dflt;
 }
+
+static void *filemap_flusher(void *arg);
 
 static int
 filemap_engine_ready(struct filemap *m)
@@ -86,8 +107,18 @@ filemap_engine_ready(struct filemap *m)
 		cfg.max_batch = (uint32_t)env_long("CMB200_MAX_BATCH", 0);
 		cfg.flags = env_long("CMB200_FINGERPRINT", 0) ? CMB200_FINGERPRINT : 0;
 		m->eng = cmb200_engine_create(&cfg);
-		if (m->eng)
+		if (m->eng) {
 			m->h_stage = cmb200_host_alloc((size_t)COMBINE_MAX * m->bsize);
+			/* ring of ~64 MiB by default, at least 64 pages */
+			long slots = env_long("CMB200_WB_SLOTS", (64L << 20) / m->bsize);
+			if (slots > 0 && slots < 64)
+				slots = 64;
+			if (slots > 0) {
+				m->wb_pages = cmb200_host_alloc((size_t)slots * m->bsize);
+				m->wb_slot = calloc((size_t)slots, sizeof(struct wb_slot));
+				m->wb_n = (m->wb_pages && m->wb_slot) ? (uint64_t)slots : 0;
+			}
+		}
 		if (!m->eng || !m->h_stage) {
 			fprintf(stderr, "cachemap_b200: cannot start the GPU engine: %s\n", cmb200_last_error());
 			if (!env_long("CMB200_SOFT_FAIL", 0)) {
@@ -97,6 +128,11 @@ filemap_engine_ready(struct filemap *m)
 			}
 			__atomic_store_n(&m->init_state, -1, __ATOMIC_RELEASE);
 		} else {
+			/* the flusher starts here, i.e. in the process that actually caches (after any fork) */
+			if (m->wb_n && pthread_create(&m->wb_thread, NULL, filemap_flusher, m) == 0)
+				m->wb_started = 1;
+			else
+				m->wb_n = 0;
 			__atomic_store_n(&m->init_state, 1, __ATOMIC_RELEASE);
 		}
 	}
@@ -124,7 +160,23 @@ filemap_create(char *destdir, uint64_t n, int compress_accel, int pshift)
 	pthread_mutex_init(&m->init_mu, NULL);
 	pthread_mutex_init(&m->q_mu, NULL);
 	pthread_cond_init(&m->q_cv, NULL);
+	pthread_mutex_init(&m->wb_mu, NULL);
+	pthread_cond_init(&m->wb_space, NULL);
+	pthread_cond_init(&m->wb_work, NULL);
+	pthread_cond_init(&m->wb_idle, NULL);
 	return m;
+}
+
+/* Waits until every page accepted so far is in the GPU store. */
+static void
+filemap_drain(struct filemap *m)
+{
+	if (!m->wb_n)
+		return;
+	pthread_mutex_lock(&m->wb_mu);
+	while (m->wb_tail != m->wb_head)
+		pthread_cond_wait(&m->wb_idle, &m->wb_mu);
+	pthread_mutex_unlock(&m->wb_mu);
 }
 
 void
@@ -132,6 +184,16 @@ filemap_free(struct filemap *m)
 {
 	if (!m)
 		return;
+	if (m->wb_started) {
+		pthread_mutex_lock(&m->wb_mu);
+		m->wb_stop = 1;
+		pthread_cond_broadcast(&m->wb_work);
+		pthread_mutex_unlock(&m->wb_mu);
+		pthread_join(m->wb_thread, NULL);      /* drains the ring first */
+	}
+	if (m->wb_pages)
+		cmb200_host_free(m->wb_pages);
+	free(m->wb_slot);
 	if (m->h_stage)
 		cmb200_host_free(m->h_stage);
 	if (m->eng)
@@ -139,15 +201,143 @@ filemap_free(struct filemap *m)
 	pthread_mutex_destroy(&m->init_mu);
 	pthread_mutex_destroy(&m->q_mu);
 	pthread_cond_destroy(&m->q_cv);
+	pthread_mutex_destroy(&m->wb_mu);
+	pthread_cond_destroy(&m->wb_space);
+	pthread_cond_destroy(&m->wb_work);
+	pthread_cond_destroy(&m->wb_idle);
 	free(m);
 }
 
-/* Runs one combined batch.  Called by the leader without q_mu held. */
+/* Makes room for `incoming` puts: while entries + incoming > capacity, retire the oldest of three
+ * random live records (cachemap.c:17-45).  Statistically the reference's policy; bitwise parity
+ * is undefined there (wall-clock timestamps, rand()). */
+static void
+filemap_make_room(struct filemap *m, uint64_t incoming)
+{
+	if (!m->capacity)
+		return;
+	for (int round = 0; round < 8; round++) {
+		uint64_t entries = cmb200_entries(m->eng);
+		if (entries + incoming <= m->capacity || entries == 0)
+			return;
+		uint64_t need = entries + incoming - m->capacity;
+		if (need > entries)
+			need = entries;
+		if (need > 1024)
+			need = 1024;    /* per round; the loop continues */
+		uint64_t *draws = malloc(3 * need * sizeof(uint64_t));
+		uint64_t *ts = malloc(3 * need * sizeof(uint64_t));
+		int32_t *ok = malloc(3 * need * sizeof(int32_t));
+		cmb200_addr *cand = malloc(3 * need * sizeof(cmb200_addr));
+		cmb200_addr *victim = malloc(need * sizeof(cmb200_addr));
+		uint64_t nv = 0;
+		if (draws && ts && ok && cand && victim) {
+			for (uint64_t i = 0; i < 3 * need; i++) {
+				uint64_t r = 0;
+				for (int b = 0; b < 64; b += 30)        /* filemap.c:271-274 */
+					r = r * ((uint64_t)RAND_MAX + 1) + (uint64_t)rand();
+				draws[i] = r;
+			}
+			if (cmb200_sample(m->eng, (size_t)(3 * need), draws, cand, ts, ok) == 0) {
+				for (uint64_t i = 0; i < need; i++) {
+					uint64_t a = ts[3 * i], b = ts[3 * i + 1], c = ts[3 * i + 2];
+					int pick;
+					if (a < b)
+						pick = (a > c) ? 2 : 0;         /* cachemap.c:29-41 */
+					else
+						pick = (b > c) ? 2 : 1;
+					if (ok[3 * i + pick])
+						victim[nv++] = cand[3 * i + pick];
+				}
+				if (nv)
+					cmb200_unset_batch(m->eng, (size_t)nv, victim);
+			}
+		}
+		free(draws); free(ts); free(ok); free(cand); free(victim);
+		if (nv == 0)
+			return;
+		if (incoming == 1)
+			return;         /* the reference evicts exactly one per put */
+	}
+}
+
+/* The flusher: takes the longest run of finished slots from the tail of the ring and puts it
+ * into the GPU store as one batch (two calls when the run wraps around the ring). */
+static void *
+filemap_flusher(void *arg)
+{
+	struct filemap *m = arg;
+	cmb200_addr *addr = malloc(FLUSH_MAX * sizeof(cmb200_addr));
+	uint64_t *ts = malloc(FLUSH_MAX * sizeof(uint64_t));
+	pthread_mutex_lock(&m->wb_mu);
+	for (;;) {
+		uint64_t count = 0;
+		while (m->wb_tail + count < m->wb_head && count < FLUSH_MAX &&
+		    m->wb_slot[(m->wb_tail + count) % m->wb_n].state == WB_READY)
+			count++;
+		if (count == 0) {
+			if (m->wb_stop && m->wb_tail == m->wb_head)
+				break;
+			pthread_cond_wait(&m->wb_work, &m->wb_mu);
+			continue;
+		}
+		for (uint64_t i = 0; i < count; i++) {
+			struct wb_slot *s = &m->wb_slot[(m->wb_tail + i) % m->wb_n];
+			s->state = WB_FLUSHING;
+			addr[i] = s->addr;
+			ts[i] = s->ts;
+		}
+		const uint64_t first = m->wb_tail % m->wb_n;
+		pthread_mutex_unlock(&m->wb_mu);
+
+		if (addr && ts) {
+			filemap_make_room(m, count);
+			uint64_t run1 = count < m->wb_n - first ? count : m->wb_n - first;
+			cmb200_put_batch(m->eng, (size_t)run1, addr, NULL, m->wb_pages + first * (size_t)m->bsize, ts, NULL);
+			if (run1 < count)
+				cmb200_put_batch(m->eng, (size_t)(count - run1), addr + run1, NULL, m->wb_pages, ts + run1, NULL);
+		}
+
+		pthread_mutex_lock(&m->wb_mu);
+		for (uint64_t i = 0; i < count; i++)
+			m->wb_slot[(m->wb_tail + i) % m->wb_n].state = WB_FREE;
+		m->wb_tail += count;
+		pthread_cond_broadcast(&m->wb_space);
+		if (m->wb_tail == m->wb_head)
+			pthread_cond_broadcast(&m->wb_idle);
+	}
+	pthread_mutex_unlock(&m->wb_mu);
+	free(addr);
+	free(ts);
+	return NULL;
+}
+
+/* Newest copy of `addr` still in the ring -> malloc()ed page, else NULL. */
+static void *
+filemap_ring_lookup(struct filemap *m, const cmb200_addr *addr)
+{
+	void *page = NULL;
+	if (!m->wb_n)
+		return NULL;
+	pthread_mutex_lock(&m->wb_mu);
+	for (uint64_t s = m->wb_head; s > m->wb_tail; s--) {
+		struct wb_slot *w = &m->wb_slot[(s - 1) % m->wb_n];
+		if (w->state >= WB_READY && w->addr.u == addr->u && w->addr.l == addr->l) {
+			page = malloc((size_t)m->bsize);
+			if (page)
+				memcpy(page, m->wb_pages + ((s - 1) % m->wb_n) * (size_t)m->bsize, (size_t)m->bsize);
+			break;
+		}
+	}
+	pthread_mutex_unlock(&m->wb_mu);
+	return page;
+}
+
+/* Runs one combined batch of gets / unsets.  Called by the leader without q_mu held. */
 static void
 filemap_run_batch(struct filemap *m, struct fm_req **reqs, int count)
 {
 	cmb200_addr addr[COMBINE_MAX];
-	uint64_t ts[COMBINE_MAX];
 	int32_t status[COMBINE_MAX];
 	int idx[COMBINE_MAX];
 	int k;
@@ -158,18 +348,6 @@ filemap_run_batch(struct filemap *m, struct fm_req **reqs, int count)
 			addr[k++] = reqs[i]->addr;
 	if (k)
 		cmb200_unset_batch(m->eng, (size_t)k, addr);
-
-	k = 0;
-	for (int i = 0; i < count; i++) {
-		if (reqs[i]->kind != REQ_SET)
-			continue;
-		addr[k] = reqs[i]->addr;
-		ts[k] = reqs[i]->ts;
-		memcpy(m->h_stage + (size_t)k * m->bsize, reqs[i]->page, (size_t)m->bsize);
-		k++;
-	}
-	if (k)
-		cmb200_put_batch(m->eng, (size_t)k, addr, NULL, m->h_stage, ts, NULL);
 
 	k = 0;
 	for (int i = 0; i < count; i++) {
@@ -234,14 +412,26 @@ filemap_set(struct filemap *m, uint128_t *key, void *value, uint64_t attr)
 {
 	if (!filemap_engine_ready(m))
 		return;
-	struct fm_req r;
-	memset(&r, 0, sizeof(r));
-	r.kind = REQ_SET;
-	r.addr.u = key->u;
-	r.addr.l = key->l;
-	r.page = value;
-	r.ts = attr;
-	filemap_submit(m, &r);
+	cmb200_addr a = { key->u, key->l };
+	if (!m->wb_n) {                         /* write-behind disabled: one synchronous GPU put */
+		filemap_make_room(m, 1);
+		cmb200_put_batch(m->eng, 1, &a, NULL, value, &attr, NULL);
+		return;
+	}
+	pthread_mutex_lock(&m->wb_mu);
+	while (m->wb_head - m->wb_tail == m->wb_n)
+		pthread_cond_wait(&m->wb_space, &m->wb_mu);     /* back-pressure: the ring is full */
+	const uint64_t s = m->wb_head++;
+	struct wb_slot *w = &m->wb_slot[s % m->wb_n];
+	w->addr = a;
+	w->ts = attr;
+	w->state = WB_FILLING;
+	pthread_mutex_unlock(&m->wb_mu);
+	memcpy(m->wb_pages + (s % m->wb_n) * (size_t)m->bsize, value, (size_t)m->bsize);
+	pthread_mutex_lock(&m->wb_mu);
+	w->state = WB_READY;
+	pthread_cond_signal(&m->wb_work);
+	pthread_mutex_unlock(&m->wb_mu);
 }
 
 void
@@ -249,6 +439,7 @@ filemap_unset(struct filemap *m, uint128_t *key)
 {
 	if (!filemap_engine_ready(m))
 		return;
+	filemap_drain(m);
 	struct fm_req r;
 	memset(&r, 0, sizeof(r));
 	r.kind = REQ_UNSET;
@@ -267,6 +458,11 @@ filemap_get(struct filemap *m, uint128_t *key)
 	r.kind = REQ_GET;
 	r.addr.u = key->u;
 	r.addr.l = key->l;
+	/* a page accepted by filemap_set but not flushed yet is served from the ring; a slot leaves
+	 * the ring only after the GPU put of its batch has completed, so nothing falls between */
+	void *page = filemap_ring_lookup(m, &r.addr);
+	if (page)
+		return page;
 	filemap_submit(m, &r);
 	if (r.bad_entry)
 		printf("bad entry\n");          /* filemap.c:237 */
@@ -278,6 +474,7 @@ filemap_get_rand(struct filemap *m, uint128_t *key, uint64_t *ts)
 {
 	if (!filemap_engine_ready(m))
 		return 0;
+	filemap_drain(m);
 	/* filemap.c:271-274: a 64-bit draw built from rand() */
 	uint64_t r = 0;
 	for (int i = 0; i < 64; i += 30)
@@ -296,30 +493,17 @@ filemap_entries(struct filemap *m)
 {
 	if (!filemap_engine_ready(m))
 		return 0;
+	filemap_drain(m);
 	return cmb200_entries(m->eng);
 }
 
 /* ------------------------------------------------------------------------------------------ */
 
-struct async_node {
-	struct async_node *next;
-	cmb200_addr addr;
-	uint64_t ts;
-	void *page;
-};
-
 struct cachemap {
-	struct filemap *pages;
+	struct filemap *pages;  /* first member, as in the reference (cachemap.h:20-21) */
 	uint64_t capacity;
 	uint64_t requests;
 	uint64_t hits;
-	/* async put queue (cachemap.c:50-105,199-216) */
-	pthread_mutex_t a_mu;
-	pthread_cond_t a_cv;
-	struct async_node *a_head, *a_tail;
-	pthread_t flusher;
-	int flusher_started;
-	int stop;
 };
 
 static uint64_t
@@ -356,64 +540,9 @@ cachemap_create(char *destdir, uint64_t capacity, int comp_accel, int pshift)
 		free(cm);
 		return NULL;
 	}
-	/* mutex and condvar exist before any thread that uses them (the reference starts its
-	 * workers first, cachemap.c:123-139, and can hang in cachemap_free because of it) */
-	pthread_mutex_init(&cm->a_mu, NULL);
-	pthread_cond_init(&cm->a_cv, NULL);
 	cm->capacity = capacity;
+	cm->pages->capacity = capacity;         /* the flusher evicts before each batch (cachemap.c:17-45) */
 	return cm;
-}
-
-/* Makes room for `incoming` puts: while entries + incoming > capacity, retire the oldest of three
- * random live records (cachemap.c:17-45).  Statistically the reference's policy; bitwise parity
- * is undefined there (wall-clock timestamps, rand()). */
-static void
-cachemap_make_room(struct cachemap *cm, uint64_t incoming)
-{
-	struct filemap *m = cm->pages;
-	for (int round = 0; round < 8; round++) {
-		uint64_t entries = filemap_entries(m);
-		if (entries + incoming <= cm->capacity || entries == 0)
-			return;
-		uint64_t need = entries + incoming - cm->capacity;
-		if (need > entries)
-			need = entries;
-		if (need > 1024)
-			need = 1024;    /* per round; the loop continues */
-		uint64_t *draws = malloc(3 * need * sizeof(uint64_t));
-		uint64_t *ts = malloc(3 * need * sizeof(uint64_t));
-		int32_t *ok = malloc(3 * need * sizeof(int32_t));
-		cmb200_addr *cand = malloc(3 * need * sizeof(cmb200_addr));
-		cmb200_addr *victim = malloc(need * sizeof(cmb200_addr));
-		uint64_t nv = 0;
-		if (draws && ts && ok && cand && victim) {
-			for (uint64_t i = 0; i < 3 * need; i++) {
-				uint64_t r = 0;
-				for (int b = 0; b < 64; b += 30)
-					r = r * ((uint64_t)RAND_MAX + 1) + (uint64_t)rand();
-				draws[i] = r;
-			}
-			if (cmb200_sample(m->eng, (size_t)(3 * need), draws, cand, ts, ok) == 0) {
-				for (uint64_t i = 0; i < need; i++) {
-					uint64_t a = ts[3 * i], b = ts[3 * i + 1], c = ts[3 * i + 2];
-					int pick;
-					if (a < b)
-						pick = (a > c) ? 2 : 0;         /* cachemap.c:29-41 */
-					else
-						pick = (b > c) ? 2 : 1;
-					if (ok[3 * i + pick])
-						victim[nv++] = cand[3 * i + pick];
-				}
-				if (nv)
-					cmb200_unset_batch(m->eng, (size_t)nv, victim);
-			}
-		}
-		free(draws); free(ts); free(ok); free(cand); free(victim);
-		if (nv == 0)
-			return;
-		if (incoming == 1)
-			return;         /* the reference evicts exactly one per put */
-	}
 }
 
 void *
@@ -436,113 +565,16 @@ cachemap_put(struct cachemap *cm, uint64_t offset, uint64_t nhid_small, uint32_t
 	cmb200_addr a;
 	if (compose_addr(cm, offset, nhid_small, genid, &a) != 0)
 		return;
-	uint64_t ts = now_ns();
-	if (!filemap_engine_ready(cm->pages))
-		return;
-	cachemap_make_room(cm, 1);
 	uint128_t key = { a.u, a.l };
-	filemap_set(cm->pages, &key, (void *)page, ts);
+	filemap_set(cm->pages, &key, (void *)page, now_ns());   /* copies the page before returning */
 }
 
-static void
-cachemap_flush_async(struct cachemap *cm, struct async_node *list)
-{
-	struct filemap *m = cm->pages;
-	cmb200_addr addr[COMBINE_MAX];
-	uint64_t ts[COMBINE_MAX];
-	/* private page-locked gather buffer: the combiner's belongs to its leader */
-	uint8_t *buf = cmb200_host_alloc((size_t)COMBINE_MAX * m->bsize);
-
-	while (list) {
-		struct async_node *first = list;
-		int k = 0;
-		while (list && k < COMBINE_MAX) {
-			addr[k] = list->addr;
-			ts[k] = list->ts;
-			if (buf)
-				memcpy(buf + (size_t)k * m->bsize, list->page, (size_t)m->bsize);
-			list = list->next;
-			k++;
-		}
-		if (buf) {
-			cachemap_make_room(cm, (uint64_t)k);
-			cmb200_put_batch(m->eng, (size_t)k, addr, NULL, buf, ts, NULL);
-		}
-		while (first != list) {
-			struct async_node *d = first;
-			first = first->next;
-			free(d->page);
-			free(d);
-		}
-	}
-	cmb200_host_free(buf);
-}
-
-static void *
-cachemap_flusher(void *arg)
-{
-	struct cachemap *cm = arg;
-	pthread_mutex_lock(&cm->a_mu);
-	while (cm->a_head || !cm->stop) {
-		if (!cm->a_head) {
-			pthread_cond_wait(&cm->a_cv, &cm->a_mu);
-			continue;
-		}
-		struct async_node *list = cm->a_head;
-		cm->a_head = cm->a_tail = NULL;
-		pthread_mutex_unlock(&cm->a_mu);
-		if (filemap_engine_ready(cm->pages)) {
-			cachemap_flush_async(cm, list);
-		} else {
-			while (list) {
-				struct async_node *d = list;
-				list = list->next;
-				free(d->page);
-				free(d);
-			}
-		}
-		pthread_mutex_lock(&cm->a_mu);
-	}
-	pthread_mutex_unlock(&cm->a_mu);
-	return NULL;
-}
-
+/* The reference copies the page and queues it for 4 worker threads (cachemap.c:199-216); here
+ * every put is already write-behind, so the two entry points are the same. */
 void
 cachemap_put_async(struct cachemap *cm, uint64_t offset, uint64_t nhid_small, uint32_t genid, const void *page)
 {
-	cmb200_addr a;
-	if (compose_addr(cm, offset, nhid_small, genid, &a) != 0)
-		return;
-	struct async_node *n = malloc(sizeof(*n));
-	if (!n)
-		return;
-	n->page = malloc((size_t)cm->pages->bsize);             /* cachemap.c:207-208 */
-	if (!n->page) {
-		free(n);
-		return;
-	}
-	memcpy(n->page, page, (size_t)cm->pages->bsize);
-	n->addr = a;
-	n->ts = now_ns();
-	n->next = NULL;
-	pthread_mutex_lock(&cm->a_mu);
-	if (!cm->flusher_started) {
-		/* started on first use, i.e. in the process that actually caches (after any fork) */
-		if (pthread_create(&cm->flusher, NULL, cachemap_flusher, cm) != 0) {
-			pthread_mutex_unlock(&cm->a_mu);
-			free(n->page);
-			free(n);
-			return;
-		}
-		cm->flusher_started = 1;
-	}
-	if (cm->a_tail)
-		cm->a_tail->next = n;
-	else
-		cm->a_head = n;
-	cm->a_tail = n;
-	pthread_cond_signal(&cm->a_cv);
-	pthread_mutex_unlock(&cm->a_mu);
+	cachemap_put(cm, offset, nhid_small, genid, page);
 }
 
 void
@@ -550,15 +582,7 @@ cachemap_free(struct cachemap *cm)
 {
 	if (!cm)
 		return;
-	pthread_mutex_lock(&cm->a_mu);
-	cm->stop = 1;
-	pthread_cond_broadcast(&cm->a_cv);
-	pthread_mutex_unlock(&cm->a_mu);
-	if (cm->flusher_started)
-		pthread_join(cm->flusher, NULL);
-	pthread_mutex_destroy(&cm->a_mu);
-	pthread_cond_destroy(&cm->a_cv);
-	filemap_free(cm->pages);
+	filemap_free(cm->pages);                /* drains the write-behind ring (cachemap.c:218-232) */
 	free(cm);
 }
 
@@ -616,7 +640,8 @@ put_batch_common(struct cachemap *cm, uint64_t n, const uint64_t *offset, const 
 		return;
 	if (batch_keys_build(cm, n, offset, nhid, genid, 1, &bk) != 0)
 		return;
-	cachemap_make_room(cm, n);
+	filemap_drain(cm->pages);               /* earlier single puts land first */
+	filemap_make_room(cm->pages, n);
 	if (on_dev)
 		cmb200_put_batch_dev(cm->pages->eng, (size_t)n, bk.addr, bk.valid, pages, bk.ts, NULL);
 	else
@@ -634,6 +659,7 @@ get_batch_common(struct cachemap *cm, uint64_t n, const uint64_t *offset, const 
 		return;
 	if (batch_keys_build(cm, n, offset, nhid, genid, 0, &bk) != 0)
 		return;
+	filemap_drain(cm->pages);
 	int32_t *status = malloc((size_t)n * 4);
 	int rc = -1;
 	if (status)
@@ -695,5 +721,8 @@ cachemap_get_counters(struct cachemap *cm, uint64_t *requests, uint64_t *hits)
 struct cmb200_engine *
 cachemap_engine(struct cachemap *cm)
 {
-	return filemap_engine_ready(cm->pages) ? cm->pages->eng : NULL;
+	if (!filemap_engine_ready(cm->pages))
+		return NULL;
+	filemap_drain(cm->pages);               /* callers of the engine see every accepted put */
+	return cm->pages->eng;
 }

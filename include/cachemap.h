@@ -9,7 +9,9 @@
  *     capacity >= 1024 pages;
  *   - cachemap_get returns a malloc()ed page of 1<<pshift bytes that the caller free()s, or NULL;
  *     `requests` counts only valid addresses, `hits` counts non-NULL returns;
- *   - cachemap_put borrows `page` for the duration of the call; cachemap_put_async copies it;
+ *   - cachemap_put borrows `page` for the duration of the call (it is copied into a page-locked
+ *     write-behind ring before the call returns; a get that follows returns it from there until
+ *     the batch it belongs to is in the GPU store); cachemap_put_async is the same call;
  *   - a page number that does not fit 44 bits is ignored (put) / NULL without counting (get);
  *   - no error codes: any internal failure is a dropped put or a miss.
  * New: all calls are thread-safe, and concurrent callers are combined into one GPU batch.
@@ -25,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PUT_THREADS	4       /* reference async worker count; here one batching flusher */
+#define PUT_THREADS	4       /* reference async worker count; here one write-behind flusher */
 
 struct cachemap;
 

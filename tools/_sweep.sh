@@ -1,1 +1,2 @@
-for cfg in "2 2 6" "2 4 6" "2 6 6" "2 4 5" "0 1 6"; do set -- $cfg; echo "mode=$1 grp_ctas=$2 enc_warps=$3"; CMB200_ENC_WARPS=$3 CMB200_ENC_MODE=$1 CMB200_GRP_CTAS_PER_SM=$2 timeout 200 python tools/kernel_bench.py --classes TB --chunks 16384 --reps 2 --fingerprint 0 2>&1 | grep -E '^[RTZMB] ' | cut -c1-45; done
+timeout 900 python -m pytest tests -m gpu -q --timeout 600 -x 2>&1 | tail -3
+timeout 600 python tools/api_threads_bench.py --per-thread 512 2>&1 | grep -v "^{" | tail -8
