@@ -280,3 +280,49 @@ def test_c_caller_links_like_edgefs(E, gpu, tmp_path):
                              timeout=200)
         assert out.returncode == 0, (pshift, out.returncode, out.stdout, out.stderr)
         assert "drop_in_test ok" in out.stdout and "ratio:" in out.stdout
+
+
+def test_write_behind_ring_wraps_and_keeps_read_your_writes(E, gpu, tmp_path):
+    """Single-page puts go through a page-locked write-behind ring.  With a ring of only 64 pages
+    and 8 writer threads the ring wraps and back-pressures many times; every get that follows a
+    put (same thread) must return that put's bytes, rewrites of one address must resolve to the
+    last one, and nothing may be lost when the map is freed and the counters read."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, os, threading
+sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
+import numpy as np, datagen, edge_fuse_b200 as E
+cm = E.Cachemap(sys.argv[1], 8192, 12, 14)          # 16 KiB pages
+bs = cm.bsize
+errs = []
+def worker(t):
+    try:
+        for i in range(300):
+            page = datagen.make_page("RTZMPA"[(t + i) % 6], bs, 1000 * t + i)
+            off = ((t * 40 + i % 40)) << 14             # 40 addresses per thread, rewritten ~7 times
+            cm.put(off, 0xABC0 + t, 0, page)
+            if i % 3 == 0:
+                back = cm.get(off, 0xABC0 + t, 0)
+                assert back == page.tobytes(), (t, i)
+    except Exception as e:
+        errs.append(repr(e))
+th = [threading.Thread(target=worker, args=(t,)) for t in range(8)]
+[x.start() for x in th]; [x.join() for x in th]
+assert not errs, errs[:3]
+for t in range(8):                                     # final contents: the last write of each address
+    for a in range(40):
+        i = max(j for j in range(300) if j % 40 == a)
+        want = datagen.make_page("RTZMPA"[(t + i) % 6], bs, 1000 * t + i).tobytes()
+        assert cm.get((t * 40 + a) << 14, 0xABC0 + t, 0) == want, (t, a)
+assert E.lib().filemap_entries(__import__("ctypes").cast(cm.h, __import__("ctypes").POINTER(__import__("ctypes").c_void_p))[0]) == 320
+rq, ht = cm.counters()
+assert rq == ht == 8 * 100 + 320, (rq, ht)
+cm.free()
+print("write-behind ok")
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CMB200_WB_SLOTS="64", CMB200_ARENA_MB="256", CMB200_MAX_BATCH="256")
+    out = subprocess.run([sys.executable, "-c", code, str(tmp_path)], cwd=root, env=env, capture_output=True,
+                         text=True, timeout=600)
+    assert out.returncode == 0 and "write-behind ok" in out.stdout, out.stdout + out.stderr

@@ -1,2 +1,2 @@
-timeout 900 python -m pytest tests -m gpu -q --timeout 600 -x 2>&1 | tail -3
-timeout 600 python tools/api_threads_bench.py --per-thread 512 2>&1 | grep -v "^{" | tail -8
+mkdir -p gpurun_out
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_encode -s 3 -c 1 -o gpurun_out/encode_r1_16k python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/ncu_full.log 2>&1; tail -1 gpurun_out/ncu_full.log
