@@ -262,7 +262,10 @@ __device__ uint32_t lz4_encode_warp(const uint8_t *__restrict__ src, uint32_t n,
 			if (en) tab.put(h, pos);                                // speculative commit
 			__syncwarp();
 			const Lz4Around ac = lz4_around(src, cand);             // latency overlaps the read-back
+			// (Lanes that share a slot store to it in the same instruction: CUDA guarantees that one
+			// of those stores lands; racecheck reports the write-write conflict, it is the mechanism.)
 			const uint32_t seen = tab.get(h);
+			__syncwarp();                                           // read-backs done before any undo store
 			const bool foreign = en && seen != (WIDE ? pos : (pos & 0xffffu));
 			const bool hit = en && !(special && lane == 0) && cand + LZ4_FAR >= pos && ac.at == pseq;
 			const uint32_t foreigns = __ballot_sync(CMB_FULL, foreign);

@@ -1,2 +1,4 @@
 mkdir -p gpurun_out
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_encode -s 3 -c 1 -o gpurun_out/encode_r1_16k python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/ncu_full.log 2>&1; tail -1 gpurun_out/ncu_full.log
+timeout 900 compute-sanitizer --tool memcheck --print-limit 20 python tools/sanitize_small.py > gpurun_out/memcheck_r1.log 2>&1; tail -5 gpurun_out/memcheck_r1.log
+timeout 900 compute-sanitizer --tool racecheck --print-limit 20 python tools/sanitize_small.py > gpurun_out/racecheck_r1.log 2>&1; tail -5 gpurun_out/racecheck_r1.log
+CMB200_ENC_MODE=1 timeout 900 compute-sanitizer --tool memcheck --print-limit 20 python tools/sanitize_small.py > gpurun_out/memcheck_groups_r1.log 2>&1; tail -3 gpurun_out/memcheck_groups_r1.log
