@@ -334,8 +334,8 @@ def run_ours(args):
                 # (16 384 chunks), from the ncu --set full capture summarised in
                 # profiles/r1_encode_notes.md (2.626 GB read + 1.288 GB written); scaled by chunk count
                 # if the launch size differs
-                "traffic": 3.914648e9 * (n / max(1, enc_launches // args.steps)) / 16384.0,
-                "traffic_source": "profiles/r1_encode_notes.md (ncu capture of round 1, not re-measured per run)",
+                "traffic": 2.004414e9 * (n / max(1, enc_launches // args.steps)) / 16384.0,
+                "traffic_source": "profiles/r1_encode_blend_ncu_details.txt (ncu --set full capture of this launch shape, round 1; not re-measured per run)",
                 "algorithmic_bytes_per_launch": alg_bytes_step / max(1, enc_launches // args.steps),
                 "avg_launch_ms": enc_ns / 1e6 / max(1, enc_launches),
                 "read_form_frac": n * CHUNK * args.steps / (enc_ns * 1e-9) / 1e9 / peak if enc_ns else 0.0,

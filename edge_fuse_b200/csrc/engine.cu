@@ -4,7 +4,7 @@
 //   key table   (slots+2) x 64 B          replaces the 32 LMDB environments (filemap.c:54-90)
 //   arena       bump-allocated records    {24-byte data_prefix, LZ4 block | raw page}
 //   page ring   2 x max_batch x bsize     double-buffered landing zone for host pages
-//   stage       max_batch x (bsize+1024)  encoder output before it is packed into the arena
+//   stage       one (bsize+1024) row per resident encoder warp: block before it is packed into the arena
 // A put batch is: H2D copy (copy stream)  ->  k_upsert  ->  k_encode (fingerprint + LZ4 + arena
 // commit + table publish), sub-batch k+1's copy overlapping sub-batch k's kernels.
 // A get batch is: k_lookup -> k_decode -> D2H copy.
@@ -101,7 +101,7 @@ extern "C" void cmb200_engine_destroy(cmb200_engine *e) {
 	cudaSetDevice(e->device);
 	if (e->st) cudaStreamSynchronize(e->st);
 	if (e->copy) cudaStreamSynchronize(e->copy);
-	cudaFree(e->table.slots); cudaFree(e->table.fp); cudaFree(e->arena.base); cudaFree(e->d_counters);
+	cudaFree(e->table.slots); cudaFree(e->table.fp); cudaFree(e->arena.base); cudaFree(e->arena.seg); cudaFree(e->d_counters);
 	cudaFree(e->d_pages[0]); cudaFree(e->d_pages[1]); cudaFree(e->d_stage);
 	cudaFree(e->d_addr); cudaFree(e->d_ts); cudaFree(e->d_valid); cudaFree(e->d_slot); cudaFree(e->d_vlen);
 	if (e->h_meta) cudaFreeHost(e->h_meta);
@@ -174,7 +174,8 @@ extern "C" cmb200_engine *cmb200_engine_create(const cmb200_config *cfg) {
 		e->stage_stride = ((uint64_t)e->bsize + 1024 + 15) & ~15ull;        // filemap.c:120 dest[bsize+1024]
 		ENG_CHECK(cudaMalloc(&e->d_pages[0], (uint64_t)e->host_batch * e->bsize + 256));
 		ENG_CHECK(cudaMalloc(&e->d_pages[1], (uint64_t)e->host_batch * e->bsize + 256));
-		ENG_CHECK(cudaMalloc(&e->d_stage, B * e->stage_stride + 256));
+		// one stage row per resident warp / group of the encode kernels (store mode), not per chunk
+		ENG_CHECK(cudaMalloc(&e->d_stage, (uint64_t)16384 * e->stage_stride + 256));
 		// small per-chunk arrays are sized for a whole slice of a call (META_CAP chunks) so that
 		// they cross PCIe once, outside the page pipeline
 		const uint64_t M = cmb200_engine::META_CAP > B ? cmb200_engine::META_CAP : B;
@@ -201,6 +202,21 @@ extern "C" cmb200_engine *cmb200_engine_create(const cmb200_config *cfg) {
 		arena = (arena + 255) & ~255ull;
 		ENG_CHECK(cudaMalloc(&e->arena.base, arena + 256));
 		e->arena.size = arena;
+		{
+			// direct encode into per-warp arena segments when the arena is large enough that
+			// 4096 segments of >= 4 worst-case records stay a small part of it
+			// (CMB200_SEG_KB overrides: 0 = always through the stage buffer)
+			const uint64_t worst = (24 + e->stage_stride + 15) & ~15ull;
+			uint64_t seg = arena / (8ull * 2072ull);
+			if (seg > (2ull << 20)) seg = 2ull << 20;
+			if (seg < 4 * worst) seg = 0;
+			const char *kb = getenv("CMB200_SEG_KB");
+			if (kb && *kb) { seg = strtoull(kb, nullptr, 10) << 10; if (seg && seg < worst) seg = worst; }
+			seg = (seg + 255) & ~255ull;
+			e->arena.seg_bytes = (uint32_t)seg;
+			ENG_CHECK(cudaMalloc(&e->arena.seg, ARENA_SEG_SLOTS * 2 * sizeof(unsigned long long)));
+			ENG_CHECK(cudaMemsetAsync(e->arena.seg, 0, ARENA_SEG_SLOTS * 2 * sizeof(unsigned long long), e->st));
+		}
 		ENG_CHECK(cudaStreamSynchronize(e->st));
 	}
 	return e;

@@ -85,4 +85,71 @@ __device__ __forceinline__ void warp_fingerprint128(const uint8_t *src, uint32_t
 	hi = ef_av(~((uint64_t)n * 0xC2B2AE3D27D4EB4FULL) + w);
 }
 
+// EF128 computed along the frontier of another pass over the same page (the LZ4 parse): stripes
+// are absorbed in order as the caller's position advances, one stripe requested ahead of need, so
+// the page crosses HBM once and the stripe loads double as a prefetch for the parse that follows
+// them.  Same result as warp_fingerprint128.
+struct EfFrontier {
+	EfLane L;
+	uint4 ahead;          // stripe `next`, already requested
+	uint32_t next;        // next stripe to absorb
+	uint32_t full;        // stripes made only of real bytes
+
+	__device__ __forceinline__ void start(const uint8_t *src, uint32_t n, int lane) {
+		ef_init(L, lane);
+		next = 0;
+		full = n >> 9;
+		ahead = full ? __ldg(reinterpret_cast<const uint4 *>(src) + lane) : make_uint4(0, 0, 0, 0);
+	}
+	__device__ __forceinline__ void take(const uint4 &x) {
+		ef_absorb(L, (uint64_t)x.x | ((uint64_t)x.y << 32), (uint64_t)x.z | ((uint64_t)x.w << 32));
+		if ((next & 15u) == 15u) ef_scramble(L);
+		next++;
+	}
+	// absorb every full stripe that starts below `pos`
+	__device__ __forceinline__ void upto(const uint8_t *src, uint32_t pos, int lane) {
+		const uint32_t target = min(full, (pos + 511u) >> 9);
+		if (next >= target) return;
+		const uint4 *v = reinterpret_cast<const uint4 *>(src) + lane;
+		take(ahead);
+		// a long match jumped ahead: single stripes up to a scramble boundary, then 16 stripes per
+		// step with 16 loads in flight, then the remainder
+		while (next < target && (next & 15u)) { const uint4 x = __ldg(v + (size_t)next * 32); take(x); }
+		while (target - next >= 16u) {
+			uint4 x[16];
+#pragma unroll
+			for (int k = 0; k < 16; k++) x[k] = __ldg(v + (size_t)(next + k) * 32);
+#pragma unroll
+			for (int k = 0; k < 16; k++)
+				ef_absorb(L, (uint64_t)x[k].x | ((uint64_t)x[k].y << 32), (uint64_t)x[k].z | ((uint64_t)x[k].w << 32));
+			ef_scramble(L);
+			next += 16;
+		}
+		while (next < target) { const uint4 x = __ldg(v + (size_t)next * 32); take(x); }
+		if (next < full) ahead = __ldg(v + (size_t)next * 32);
+	}
+	// absorb the rest of the page (incl. a zero-padded partial stripe) and fold the lanes
+	__device__ __forceinline__ void finish(const uint8_t *src, uint32_t n, int lane, uint64_t &hi, uint64_t &lo) {
+		upto(src, n, lane);                               // all full stripes
+		const uint32_t stripes = (n + 511u) >> 9;
+		if (next < stripes) {                             // partial last stripe
+			const uint32_t off = next * 512u + lane * 16u;
+			uint64_t x0 = 0, x1 = 0;
+			for (uint32_t k = 0; k < 16 && off + k < n; k++) {
+				const uint64_t byte = ldg8(src + off + k);
+				if (k < 8) x0 |= byte << (8 * k); else x1 |= byte << (8 * (k - 8));
+			}
+			ef_absorb(L, x0, x1);
+			if ((next & 15u) == 15u) ef_scramble(L);
+			next++;
+		}
+		uint64_t u = ef_fold(L.a ^ L.s0, L.b ^ L.s1);
+		uint64_t w = ef_fold(L.a ^ L.s3, L.b ^ L.s2);
+		u = warp_sum_u64(u);
+		w = warp_sum_u64(w);
+		lo = ef_av((uint64_t)n * 0x9E3779B185EBCA87ULL + u);
+		hi = ef_av(~((uint64_t)n * 0xC2B2AE3D27D4EB4FULL) + w);
+	}
+};
+
 }  // namespace cmb

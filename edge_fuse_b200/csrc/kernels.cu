@@ -259,11 +259,56 @@ __device__ void commit_record(const EncodeJob &job, uint32_t i, uint32_t idx, co
 	}
 }
 
+// Direct variant of commit_record: the block already sits in the arena at `base + 24` (this warp's
+// segment cursor).  A new key simply keeps it there; a rewrite whose old record is large enough is
+// copied over the old record so that rewrites do not consume arena.  Returns the bytes of the
+// segment consumed (0 when the old record was reused).
+__device__ uint32_t commit_direct(const EncodeJob &job, uint32_t i, uint32_t idx, unsigned long long base,
+    uint32_t clen, uint64_t fp_hi, uint64_t fp_lo, int lane) {
+	Slot &s = job.table.slots[idx];
+	const uint32_t need = (24u + clen + 15u) & ~15u;
+	unsigned long long rec = base;
+	int reuse = 0;
+	if (lane == 0) {
+		if (s.alloc >= need) { rec = s.rec_off; reuse = 1; }
+		else {
+			if (s.alloc) atomicAdd(job.arena.garbage, (unsigned long long)s.alloc);
+			s.alloc = need; s.rec_off = base;
+		}
+	}
+	reuse = __shfl_sync(CMB_FULL, reuse, 0);
+	rec = __shfl_sync(CMB_FULL, rec, 0);
+	uint8_t *r = job.arena.base + rec;
+	if (reuse) { warp_copy_rw(r + 24, job.arena.base + base + 24, clen, lane); }
+	const unsigned long long au = job.addr[2 * i], al = job.addr[2 * i + 1];
+	if (lane < 6) {
+		const uint32_t w = lane == 0 ? (uint32_t)au : lane == 1 ? (uint32_t)(au >> 32) : lane == 2 ? (uint32_t)al
+		    : lane == 3 ? (uint32_t)(al >> 32) : lane == 4 ? clen : 0u;
+		reinterpret_cast<uint32_t *>(r)[lane] = w;
+	}
+	__syncwarp();
+	if (lane == 0) {
+		if (s.owner) { atomicAdd(job.table.remote, (unsigned long long)-1ll); s.owner = 0; }
+		s.addr_u = au; s.addr_l = al;
+		s.ts = job.ts ? job.ts[i] : 0;
+		if (job.table.fp) { job.table.fp[2 * (size_t)idx] = fp_hi; job.table.fp[2 * (size_t)idx + 1] = fp_lo; }
+		if (s.vlen == 0) atomicAdd(job.table.entries, 1ull);
+		s.vlen = clen + 1u;
+	}
+	return reuse ? 0u : need;
+}
+
 template <bool WIDE>
 __global__ void __launch_bounds__(512, 1) k_encode(EncodeJob job) {
 	extern __shared__ __align__(16) uint8_t smem[];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	uint8_t *wsm = smem + (size_t)warp * LZ4_TABLE_BYTES;
+	const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + warp;         // resident warp slot
+	const bool direct = job.slot_idx != nullptr && job.arena.seg_bytes != 0u && job.accel != 0u && gw < ARENA_SEG_SLOTS;
+	// room one chunk may need while it is being encoded: prefix + a stage row (filemap.c:120 dest[bsize+1024])
+	const uint32_t worst = (uint32_t)((24u + job.stage_stride + 15u) & ~15ull);
+	unsigned long long seg_cur = 0, seg_end = 0;                         // lane 0's copy is the truth
+	if (direct && lane == 0) { seg_cur = job.arena.seg[2 * gw]; seg_end = job.arena.seg[2 * gw + 1]; }
 	for (;;) {
 		uint32_t i = 0;
 		if (lane == 0) i = atomicAdd(job.work, 1u);
@@ -279,23 +324,55 @@ __global__ void __launch_bounds__(512, 1) k_encode(EncodeJob job) {
 		}
 		const uint8_t *src = job.pages + (size_t)i * job.page_stride;
 		uint64_t fp_hi = 0, fp_lo = 0;
-		if (job.fps) {
-			warp_fingerprint128(src, job.nbytes, lane, fp_hi, fp_lo);
-			if (lane == 0) { job.fps[2 * (size_t)i] = fp_hi; job.fps[2 * (size_t)i + 1] = fp_lo; }
-		}
 		if (job.accel == 0) {           // comp_accel == 0: raw page, compressed_length 0 (filemap.c:129-133)
+			if (job.fps) {
+				warp_fingerprint128(src, job.nbytes, lane, fp_hi, fp_lo);
+				if (lane == 0) { job.fps[2 * (size_t)i] = fp_hi; job.fps[2 * (size_t)i + 1] = fp_lo; }
+			}
 			if (lane == 0) job.lens[i] = 0;
 			if (store) commit_record(job, i, idx, src, job.nbytes, 0, true, fp_hi, fp_lo, lane);
 			continue;
 		}
-		uint8_t *dst = job.stage + (size_t)i * job.stage_stride;
-		uint32_t clen = lz4_encode_warp<WIDE>(src, job.nbytes, dst, job.accel, wsm, lane);
+		// store mode: the block only passes through the stage on its way into the arena, so each warp
+		// reuses ONE stage row instead of a row per chunk; with a large arena it does not even do
+		// that: the block is encoded straight into this warp's arena segment
+		uint8_t *dst = job.stage + (size_t)(store ? gw : i) * job.stage_stride;
+		unsigned long long base = 0;
+		int in_arena = 0;
+		if (direct) {
+			if (lane == 0) {
+				if (seg_cur + worst > seg_end) {             // segment exhausted: take the next one
+					if (seg_end > seg_cur) atomicAdd(job.arena.garbage, seg_end - seg_cur);
+					const unsigned long long off = atomicAdd(job.arena.head, (unsigned long long)job.arena.seg_bytes);
+					if (off + job.arena.seg_bytes <= job.arena.size) { seg_cur = off; seg_end = off + job.arena.seg_bytes; }
+					else { atomicAdd(job.arena.head, (unsigned long long)-(long long)job.arena.seg_bytes); seg_cur = seg_end = 0; }
+				}
+				in_arena = seg_cur + worst <= seg_end;
+				base = seg_cur;
+			}
+			in_arena = __shfl_sync(CMB_FULL, in_arena, 0);
+			base = __shfl_sync(CMB_FULL, base, 0);
+			if (in_arena) dst = job.arena.base + base + 24;
+		}
+		uint32_t clen;
+		if (job.fps) {                  // fingerprint along the parse frontier: the page is read once
+			clen = lz4_encode_warp<WIDE, true>(src, job.nbytes, dst, job.accel, wsm, lane, fp_hi, fp_lo);
+			if (lane == 0) { job.fps[2 * (size_t)i] = fp_hi; job.fps[2 * (size_t)i + 1] = fp_lo; }
+		} else {
+			clen = lz4_encode_warp<WIDE, false>(src, job.nbytes, dst, job.accel, wsm, lane, fp_hi, fp_lo);
+		}
 		if (lane == 0) job.lens[i] = (int32_t)clen;
 		if (store) {
 			__syncwarp();
-			commit_record(job, i, idx, dst, clen, (int32_t)clen, false, fp_hi, fp_lo, lane);
+			if (in_arena) {
+				const uint32_t used = commit_direct(job, i, idx, base, clen, fp_hi, fp_lo, lane);
+				if (lane == 0) seg_cur += used;
+			} else {
+				commit_record(job, i, idx, dst, clen, (int32_t)clen, false, fp_hi, fp_lo, lane);
+			}
 		}
 	}
+	if (direct && lane == 0) { job.arena.seg[2 * gw] = seg_cur; job.arena.seg[2 * gw + 1] = seg_end; }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -383,7 +460,7 @@ __global__ void __launch_bounds__(128, 6) k_encode_groups(EncodeJob job) {
 					live = sidx != 0xffffffffu && job.table.slots[sidx].seq == job.seq0 + job.seq_stride * i;
 				}
 				src = job.pages + (size_t)i * job.page_stride;
-				dst = job.stage + (size_t)i * job.stage_stride;
+				dst = job.stage + (size_t)(store ? ggroup : i) * job.stage_stride;
 				if (!live) {
 					if (g.gl == 0) job.lens[i] = -1;
 				} else if (accel == 0) {       // raw page, compressed_length 0 (filemap.c:129-133)

@@ -33,12 +33,18 @@ struct TableView {
 	uint64_t *fp;                // optional, 2 x u64 per slot {hi, lo}
 };
 
+#define ARENA_SEG_SLOTS 4096u    // resident encoder warps that can own an arena segment
+
 struct ArenaView {
 	uint8_t *base;
 	uint64_t size;
 	unsigned long long *head;     // bump pointer
 	unsigned long long *garbage;  // bytes orphaned by relocated / deleted records
 	unsigned long long *dropped;  // puts dropped because the arena was full (filemap.c:154-157 analogue)
+	// direct encode (large arenas): every resident encoder warp owns a segment of the arena and
+	// writes blocks straight into it; seg[2w] = cursor, seg[2w+1] = end of warp slot w's segment
+	unsigned long long *seg;
+	uint32_t seg_bytes;           // segment size, 0 = blocks go through the stage buffer instead
 };
 
 enum LookupStatus : int32_t {

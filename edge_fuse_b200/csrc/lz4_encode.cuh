@@ -33,6 +33,7 @@
 //     the stall samples waiting on instruction fetch): rare paths are __noinline__.
 #pragma once
 #include "common.cuh"
+#include "fingerprint.cuh"
 
 namespace cmb {
 
@@ -209,13 +210,17 @@ __device__ __noinline__ uint32_t lz4_emit_general(uint8_t *dst, uint32_t op, con
 // Encodes src[0,n) into dst; returns the block length (uniform across the warp).
 // `smem` is this warp's LZ4_TABLE_BYTES of shared memory.  src must be 4-byte aligned and
 // readable up to 16 bytes past src+n (the library's page buffers are contiguous and padded).
-template <bool WIDE>
+// With FP the EF128 fingerprint of the page is computed along the way (EfFrontier): the parse and
+// the fingerprint then read the page from HBM once, and the stripe loads prefetch the parse.
+template <bool WIDE, bool FP>
 __device__ uint32_t lz4_encode_warp(const uint8_t *__restrict__ src, uint32_t n, uint8_t *__restrict__ dst,
-    uint32_t accel, uint8_t *smem, int lane) {
+    uint32_t accel, uint8_t *smem, int lane, uint64_t &fp_hi, uint64_t &fp_lo) {
 	Lz4Table<WIDE> tab;
 	tab.t = reinterpret_cast<decltype(tab.t)>(smem);
 	const uint32_t lim4 = (n + 3u) & ~3u;
 	uint32_t op = 0, anchor = 0;
+	EfFrontier fp;
+	if (FP) fp.start(src, n, lane);
 
 	// lz4.c:739 — table cleared per call: an untouched slot aliases position 0.
 	{
@@ -239,6 +244,7 @@ __device__ uint32_t lz4_encode_warp(const uint8_t *__restrict__ src, uint32_t n,
 		// first batch of the chunk: plain search from position 1 (lz4.c:584), no refill / re-test
 		uint32_t shift = 0;          // 2 once a match has ended
 		for (;;) {
+			if (FP) fp.upto(src, anchor + 512u, lane);     // stripes ahead of this batch's probes
 			const bool special = (uint32_t)lane < shift;
 			uint32_t pos;
 			bool en;
@@ -356,6 +362,7 @@ __device__ uint32_t lz4_encode_warp(const uint8_t *__restrict__ src, uint32_t n,
 	if (run >= 15u) op = lz4_emit_len(dst, op, run - 15u, lane);
 	lz4_copy_literals(dst + op, src + anchor, run, lane);
 	op += run;
+	if (FP) fp.finish(src, n, lane, fp_hi, fp_lo);
 	return op;
 }
 

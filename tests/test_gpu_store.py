@@ -326,3 +326,42 @@ print("write-behind ok")
     out = subprocess.run([sys.executable, "-c", code, str(tmp_path)], cwd=root, env=env, capture_output=True,
                          text=True, timeout=600)
     assert out.returncode == 0 and "write-behind ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_direct_arena_segments(gpu):
+    """Large arenas take the direct path: blocks are encoded straight into per-warp arena segments
+    (kernels.cu commit_direct) instead of passing through the stage buffer.  CMB200_SEG_KB forces
+    small segments so that they roll over many times; records, lengths, rewrites in place and
+    read-back must be what the staged path gives."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import sys, os
+sys.path.insert(0, os.getcwd())
+import numpy as np, edge_fuse_b200 as E
+from oracle import ef_oracle as O
+n = 3000
+eng = E.Engine(pshift=16, accel=12, capacity=8192, arena_bytes=2 << 30, max_batch=1024, flags=E.FINGERPRINT)
+u = np.full(n, 9, dtype=np.uint64); l = np.arange(n, dtype=np.uint64)
+used = []
+for rnd in range(3):                       # round 0 allocates, round 1 rewrites the same content, round 2 other content
+    pages = np.stack([E.gen_chunk_host(7 + (rnd == 2), c, 65536) for c in range(n)])
+    lens = eng.put(u, l, pages)
+    st = eng.stats(); used.append((st["arena_used"], st["arena_garbage"]))
+    out, status = eng.get(u, l)
+    assert (status == E.HIT).all() and (out == pages).all(), rnd
+    recs = eng.read_records(u, l)
+    for k in list(range(0, n, 83)) + [n - 1]:
+        blk = O.lz4_encode(pages[k], 12)
+        assert recs[k][24:] == blk and recs[k][:16] == np.array([9, k], dtype=np.uint64).tobytes(), (rnd, k)
+        assert int(lens[k]) == len(blk) == int.from_bytes(recs[k][16:20], "little"), (rnd, k)
+    fps, ok = eng.read_fingerprints(u, l)
+    assert ok.all() and (int(fps[5, 0]), int(fps[5, 1])) == O.fingerprint128(pages[5])
+st = eng.stats()
+assert st["entries"] == n and st["dropped_puts"] == 0 and st["arena_used"] <= (2 << 30), st
+print("direct ok", used)
+'''
+    env = dict(os.environ, CMB200_SEG_KB="320")
+    out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "direct ok" in out.stdout, out.stdout + out.stderr

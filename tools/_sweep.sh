@@ -1,4 +1,5 @@
 mkdir -p gpurun_out
-timeout 900 compute-sanitizer --tool memcheck --print-limit 20 python tools/sanitize_small.py > gpurun_out/memcheck_r1.log 2>&1; tail -5 gpurun_out/memcheck_r1.log
-timeout 900 compute-sanitizer --tool racecheck --print-limit 20 python tools/sanitize_small.py > gpurun_out/racecheck_r1.log 2>&1; tail -5 gpurun_out/racecheck_r1.log
-CMB200_ENC_MODE=1 timeout 900 compute-sanitizer --tool memcheck --print-limit 20 python tools/sanitize_small.py > gpurun_out/memcheck_groups_r1.log 2>&1; tail -3 gpurun_out/memcheck_groups_r1.log
+timeout 1200 python -m pytest tests -m gpu -q --timeout 900 -x 2>&1 | tail -3
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_encode -s 3 -c 1 -o gpurun_out/encode_r1_16k_c python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/ncu_full.log 2>&1; tail -1 gpurun_out/ncu_full.log
+timeout 600 python bench.py --steps 4 --warmup 3 --no-cpu 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print({k:d[k] for k in ('value','ms_per_step','e2e')}, d['roofline']['frac'])"
+CMB200_SEG_KB=0 timeout 600 python bench.py --steps 4 --warmup 3 --no-cpu 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('staged', {k:d[k] for k in ('value','ms_per_step','e2e')}, d['roofline']['frac'])"
