@@ -19,6 +19,7 @@ EXPORTED_SYMBOLS = [
     "cachemap_create", "cachemap_free", "cachemap_get", "cachemap_put", "cachemap_put_async",
     "cachemap_print_stats", "cachemap_put_batch", "cachemap_get_batch", "cachemap_put_batch_dev",
     "cachemap_get_batch_dev", "cachemap_get_counters", "cachemap_engine",
+    "cachemap_read_range", "cachemap_write_range",
     # filemap.h — reference cachemap/filemap.h:19-29
     "filemap_create", "filemap_free", "filemap_set", "filemap_unset", "filemap_get",
     "filemap_get_rand", "filemap_entries",
@@ -26,7 +27,7 @@ EXPORTED_SYMBOLS = [
     "cmb200_last_error", "cmb200_device_count", "cmb200_engine_create", "cmb200_engine_destroy",
     "cmb200_host_alloc", "cmb200_host_free", "cmb200_dev_alloc", "cmb200_dev_free",
     "cmb200_memcpy_h2d", "cmb200_memcpy_d2h", "cmb200_stream", "cmb200_sync",
-    "cmb200_put_batch", "cmb200_put_batch_dev", "cmb200_get_batch", "cmb200_get_batch_dev",
+    "cmb200_put_batch", "cmb200_put_batch_dev", "cmb200_put_batch_async", "cmb200_wait", "cmb200_get_batch", "cmb200_get_batch_dev",
     "cmb200_unset_batch", "cmb200_entries", "cmb200_sample", "cmb200_read_records",
     "cmb200_read_fingerprints", "cmb200_get_stats", "cmb200_compose_keys",
     "cmb200_set_stream_order", "cmb200_import_remote", "cmb200_locate_batch",
@@ -78,6 +79,8 @@ def lib() -> C.CDLL:
         "cachemap_get_batch_dev": (None, [vp, u64, vp, vp, vp, vp, vp]),
         "cachemap_get_counters": (None, [vp, vp, vp]),
         "cachemap_engine": (vp, [vp]),
+        "cachemap_read_range": (i32, [vp, u64, u32, u64, sz, vp]),
+        "cachemap_write_range": (None, [vp, u64, u32, u64, sz, vp]),
         "filemap_create": (vp, [C.c_char_p, u64, i32, i32]),
         "filemap_free": (None, [vp]),
         "filemap_set": (None, [vp, vp, vp, u64]),
@@ -99,6 +102,8 @@ def lib() -> C.CDLL:
         "cmb200_sync": (i32, [vp]),
         "cmb200_put_batch": (i32, [vp, sz, vp, vp, vp, vp, vp]),
         "cmb200_put_batch_dev": (i32, [vp, sz, vp, vp, vp, vp, vp]),
+        "cmb200_put_batch_async": (i32, [vp, sz, vp, vp, vp, vp, vp, vp]),
+        "cmb200_wait": (i32, [vp, u64]),
         "cmb200_get_batch": (i32, [vp, sz, vp, vp, vp, vp]),
         "cmb200_get_batch_dev": (i32, [vp, sz, vp, vp, vp, vp]),
         "cmb200_unset_batch": (i32, [vp, sz, vp]),
@@ -273,6 +278,20 @@ class Engine:
         _check(fn(self.h, n, _ptr(addr), _ptr(valid), _ptr(pages), _ptr(ts), _ptr(lens)), "cmb200_put_batch")
         return lens
 
+    def put_async(self, u, l, pages, ts=None, valid=None, lens=None) -> int:
+        """cmb200_put_batch_async -> ticket for wait().  pages are host memory; `lens`, if given,
+        must be page-locked int32 storage that stays alive until wait(ticket)."""
+        addr = _addr_array(u, l)
+        ts = None if ts is None else np.ascontiguousarray(ts, dtype=np.uint64)
+        valid = None if valid is None else np.ascontiguousarray(valid, dtype=np.uint8)
+        t = C.c_uint64(0)
+        _check(lib().cmb200_put_batch_async(self.h, len(addr), _ptr(addr), _ptr(valid), _ptr(pages), _ptr(ts),
+                                            _ptr(lens), C.byref(t)), "cmb200_put_batch_async")
+        return t.value
+
+    def wait(self, ticket: int):
+        _check(lib().cmb200_wait(self.h, ticket), "cmb200_wait")
+
     def get(self, u, l, valid=None, out=None, on_dev=False):
         addr = _addr_array(u, l)
         n = len(addr)
@@ -422,6 +441,17 @@ class Cachemap:
         fn = lib().cachemap_get_batch_dev if on_dev else lib().cachemap_get_batch
         fn(self.h, n, _ptr(offset), _ptr(nhid), _ptr(genid), _ptr(out), _ptr(hit))
         return out, hit
+
+    def read_range(self, nhid: int, genid: int, off: int, size: int):
+        """The page loop of edgefs_read (edgefs.c:1159-1178) as one call -> bytes or None."""
+        out = np.zeros(max(size, 1), dtype=np.uint8)
+        ok = lib().cachemap_read_range(self.h, nhid, genid, off, size, _ptr(out))
+        return out[:size].tobytes() if ok else None
+
+    def write_range(self, nhid: int, genid: int, off: int, data):
+        """The put loop of edgefs_read's miss path / edgefs_write (edgefs.c:1183-1195,1216-1228)."""
+        data = np.ascontiguousarray(np.frombuffer(data, dtype=np.uint8) if isinstance(data, (bytes, bytearray)) else data)
+        lib().cachemap_write_range(self.h, nhid, genid, off, data.size, _ptr(data))
 
     def counters(self):
         rq, ht = C.c_uint64(), C.c_uint64()

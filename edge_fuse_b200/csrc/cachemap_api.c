@@ -41,7 +41,8 @@ enum wb_state { WB_FREE = 0, WB_FILLING, WB_READY, WB_FLUSHING };
 struct fm_req {
 	enum req_kind kind;
 	cmb200_addr addr;
-	void *out;              /* REQ_GET: malloc()ed page or NULL */
+	void *out;              /* REQ_GET: malloc()ed page (or dst) on a hit, else NULL */
+	void *dst;              /* REQ_GET: caller's buffer to fill instead of malloc()ing one */
 	int bad_entry;
 	int done;
 	struct fm_req *next;
@@ -314,7 +315,7 @@ filemap_flusher(void *arg)
 
 /* Newest copy of `addr` still in the ring -> malloc()ed page, else NULL. */
 static void *
-filemap_ring_lookup(struct filemap *m, const cmb200_addr *addr)
+filemap_ring_lookup(struct filemap *m, const cmb200_addr *addr, void *dst)
 {
 	void *page = NULL;
 	if (!m->wb_n)
@@ -323,7 +324,7 @@ filemap_ring_lookup(struct filemap *m, const cmb200_addr *addr)
 	for (uint64_t s = m->wb_head; s > m->wb_tail; s--) {
 		struct wb_slot *w = &m->wb_slot[(s - 1) % m->wb_n];
 		if (w->state >= WB_READY && w->addr.u == addr->u && w->addr.l == addr->l) {
-			page = malloc((size_t)m->bsize);
+			page = dst ? dst : malloc((size_t)m->bsize);
 			if (page)
 				memcpy(page, m->wb_pages + ((s - 1) % m->wb_n) * (size_t)m->bsize, (size_t)m->bsize);
 			break;
@@ -361,7 +362,7 @@ filemap_run_batch(struct filemap *m, struct fm_req **reqs, int count)
 		for (int j = 0; j < k; j++) {
 			struct fm_req *r = reqs[idx[j]];
 			if (status[j] == CMB200_HIT) {
-				r->out = malloc((size_t)m->bsize);      /* filemap.c:242 */
+				r->out = r->dst ? r->dst : malloc((size_t)m->bsize);    /* filemap.c:242 */
 				if (r->out)
 					memcpy(r->out, m->h_stage + (size_t)j * m->bsize, (size_t)m->bsize);
 			} else if (status[j] == CMB200_BAD_ENTRY) {
@@ -371,16 +372,21 @@ filemap_run_batch(struct filemap *m, struct fm_req **reqs, int count)
 	}
 }
 
+/* Queues `count` requests (an array) and returns when all of them have been served.  The queue is
+ * FIFO and batches complete in order, so the last request finishing means all have. */
 static void
-filemap_submit(struct filemap *m, struct fm_req *req)
+filemap_submit_many(struct filemap *m, struct fm_req *reqs, int count)
 {
-	req->done = 0;
-	req->next = NULL;
+	for (int i = 0; i < count; i++) {
+		reqs[i].done = 0;
+		reqs[i].next = i + 1 < count ? &reqs[i + 1] : NULL;
+	}
+	struct fm_req *req = &reqs[count - 1];
 	pthread_mutex_lock(&m->q_mu);
 	if (m->q_tail)
-		m->q_tail->next = req;
+		m->q_tail->next = &reqs[0];
 	else
-		m->q_head = req;
+		m->q_head = &reqs[0];
 	m->q_tail = req;
 	while (!req->done) {
 		if (m->leader_active) {
@@ -405,6 +411,12 @@ filemap_submit(struct filemap *m, struct fm_req *req)
 		pthread_cond_broadcast(&m->q_cv);
 	}
 	pthread_mutex_unlock(&m->q_mu);
+}
+
+static void
+filemap_submit(struct filemap *m, struct fm_req *req)
+{
+	filemap_submit_many(m, req, 1);
 }
 
 void
@@ -460,7 +472,7 @@ filemap_get(struct filemap *m, uint128_t *key)
 	r.addr.l = key->l;
 	/* a page accepted by filemap_set but not flushed yet is served from the ring; a slot leaves
 	 * the ring only after the GPU put of its batch has completed, so nothing falls between */
-	void *page = filemap_ring_lookup(m, &r.addr);
+	void *page = filemap_ring_lookup(m, &r.addr, NULL);
 	if (page)
 		return page;
 	filemap_submit(m, &r);
@@ -644,8 +656,12 @@ put_batch_common(struct cachemap *cm, uint64_t n, const uint64_t *offset, const 
 	filemap_make_room(cm->pages, n);
 	if (on_dev)
 		cmb200_put_batch_dev(cm->pages->eng, (size_t)n, bk.addr, bk.valid, pages, bk.ts, NULL);
-	else
-		cmb200_put_batch(cm->pages->eng, (size_t)n, bk.addr, bk.valid, pages, bk.ts, NULL);
+	else {
+		/* write-behind like cachemap_put: back when the pages have crossed to the GPU and the
+		 * caller may reuse them; whatever is called next is ordered after the encode */
+		uint64_t ticket;
+		cmb200_put_batch_async(cm->pages->eng, (size_t)n, bk.addr, bk.valid, pages, bk.ts, NULL, &ticket);
+	}
 	batch_keys_free(&bk);
 }
 
@@ -709,6 +725,88 @@ cachemap_get_batch_dev(struct cachemap *cm, uint64_t n, const uint64_t *offset, 
     const uint32_t *genid, void *pages_out_dev, uint8_t *hit_out)
 {
 	get_batch_common(cm, n, offset, nhid_small, genid, pages_out_dev, hit_out, 1);
+}
+
+/* ---- request ranges (edgefs.c:1159-1195, 1216-1228) ------------------------------------------ */
+
+int
+cachemap_read_range(struct cachemap *cm, uint64_t nhid_small, uint32_t genid, uint64_t off, size_t size,
+    void *out_buf)
+{
+	const int pshift = cm->pages->pshift;
+	const uint64_t page_size = 1ULL << pshift;
+	if ((off & (page_size - 1)) || ((off + (uint64_t)size) & (page_size - 1)))     /* edgefs.c:192-203 */
+		return 0;
+	const uint64_t n = (uint64_t)size >> pshift;
+	if (n == 0)
+		return 1;
+	if (!filemap_engine_ready(cm->pages))
+		return 0;
+	struct fm_req *reqs = calloc((size_t)n, sizeof(*reqs));
+	int *which = malloc((size_t)n * sizeof(int));
+	uint8_t *state = calloc((size_t)n, 1);          /* 0 miss, 1 hit, 2 invalid address */
+	if (!reqs || !which || !state) {
+		free(reqs); free(which); free(state);
+		return 0;
+	}
+	/* pages still in the write-behind ring are served from it, the rest go to the GPU as one
+	 * chain of requests (one batch unless the chain is longer than COMBINE_MAX) */
+	int k = 0;
+	for (uint64_t i = 0; i < n; i++) {
+		cmb200_addr a;
+		uint8_t *dst = (uint8_t *)out_buf + (i << pshift);
+		if (compose_addr(cm, off + (i << pshift), nhid_small, genid, &a) != 0) {
+			state[i] = 2;
+			continue;
+		}
+		if (filemap_ring_lookup(cm->pages, &a, dst)) {
+			state[i] = 1;
+			continue;
+		}
+		reqs[k].kind = REQ_GET;
+		reqs[k].addr = a;
+		reqs[k].dst = dst;
+		which[k] = (int)i;
+		k++;
+	}
+	if (k)
+		filemap_submit_many(cm->pages, reqs, k);
+	for (int j = 0; j < k; j++) {
+		if (reqs[j].out)
+			state[which[j]] = 1;
+	}
+	/* counters as the reference's loop leaves them: it stops at the first page that is not a
+	 * hit; an invalid address returns NULL without counting a request (cachemap.c:173-174) */
+	uint64_t rq = 0, ht = 0, i = 0;
+	for (; i < n; i++) {
+		if (state[i] == 2)
+			break;
+		rq++;
+		if (state[i] != 1)
+			break;
+		ht++;
+	}
+	for (int j = 0; j < k; j++)
+		if (reqs[j].bad_entry && (uint64_t)which[j] <= i)
+			printf("bad entry\n");                  /* filemap.c:237 */
+	__atomic_fetch_add(&cm->requests, rq, __ATOMIC_RELAXED);
+	__atomic_fetch_add(&cm->hits, ht, __ATOMIC_RELAXED);
+	free(reqs); free(which); free(state);
+	return i == n;
+}
+
+void
+cachemap_write_range(struct cachemap *cm, uint64_t nhid_small, uint32_t genid, uint64_t off, size_t size,
+    const void *data)
+{
+	const int pshift = cm->pages->pshift;
+	const uint64_t page_size = 1ULL << pshift;
+	if ((off & (page_size - 1)) || ((off + (uint64_t)size) & (page_size - 1)))     /* edgefs.c:192-203 */
+		return;
+	/* every put is write-behind (one memcpy into the page-locked ring), so the loop of
+	 * edgefs.c:1186-1190 / 1219-1223 already hands the GPU one batch */
+	for (uint64_t i = 0; i < ((uint64_t)size >> pshift); i++)
+		cachemap_put(cm, off + (i << pshift), nhid_small, genid, (const uint8_t *)data + (i << pshift));
 }
 
 void

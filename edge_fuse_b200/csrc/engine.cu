@@ -60,6 +60,17 @@ struct cmb200_engine {
 	// per-launch device timing of the dominant kernels (roofline evidence for bench.py)
 	static constexpr int RING = 64;
 	cudaEvent_t t0[RING] = {}, t1[RING] = {};
+	// asynchronous puts (cmb200_put_batch_async): kernel timing events not harvested yet are
+	// p0/p1[pend_tail .. pend_head), completion tickets are events on the compute stream
+	cudaEvent_t p0[RING] = {}, p1[RING] = {};
+	uint64_t pend_head = 0, pend_tail = 0;
+	static constexpr int TICKETS = 8;
+	cudaEvent_t ticket_ev[TICKETS] = {};
+	uint64_t tickets = 0;
+	cudaEvent_t meta_done = nullptr, meta_free[2] = {nullptr, nullptr};
+	uint64_t ring_pos = 0;               // page ring buffer in turn, kept across calls
+	uint64_t meta_pos = 0;               // same for the two copies of d_addr / d_ts / d_valid (host puts)
+	size_t meta_cap = 0;                 // entries per copy
 	std::mutex mu;
 	cmb200_stats stats{};
 };
@@ -113,7 +124,12 @@ extern "C" void cmb200_engine_destroy(cmb200_engine *e) {
 	for (int i = 0; i < cmb200_engine::RING; i++) {
 		if (e->t0[i]) cudaEventDestroy(e->t0[i]);
 		if (e->t1[i]) cudaEventDestroy(e->t1[i]);
+		if (e->p0[i]) cudaEventDestroy(e->p0[i]);
+		if (e->p1[i]) cudaEventDestroy(e->p1[i]);
 	}
+	for (int i = 0; i < cmb200_engine::TICKETS; i++) if (e->ticket_ev[i]) cudaEventDestroy(e->ticket_ev[i]);
+	if (e->meta_done) cudaEventDestroy(e->meta_done);
+	for (int i = 0; i < 2; i++) if (e->meta_free[i]) cudaEventDestroy(e->meta_free[i]);
 	if (e->st) cudaStreamDestroy(e->st);
 	if (e->copy) cudaStreamDestroy(e->copy);
 	delete e;
@@ -155,7 +171,14 @@ extern "C" cmb200_engine *cmb200_engine_create(const cmb200_config *cfg) {
 		for (int i = 0; i < cmb200_engine::RING; i++) {
 			ENG_CHECK(cudaEventCreate(&e->t0[i]));
 			ENG_CHECK(cudaEventCreate(&e->t1[i]));
+			ENG_CHECK(cudaEventCreate(&e->p0[i]));
+			ENG_CHECK(cudaEventCreate(&e->p1[i]));
 		}
+		for (int i = 0; i < cmb200_engine::TICKETS; i++)
+			ENG_CHECK(cudaEventCreateWithFlags(&e->ticket_ev[i], cudaEventDisableTiming));
+		ENG_CHECK(cudaEventCreateWithFlags(&e->meta_done, cudaEventDisableTiming));
+		ENG_CHECK(cudaEventCreateWithFlags(&e->meta_free[0], cudaEventDisableTiming));
+		ENG_CHECK(cudaEventCreateWithFlags(&e->meta_free[1], cudaEventDisableTiming));
 		ENG_CHECK(cudaMalloc(&e->table.slots, (slots + 2) * sizeof(Slot)));
 		ENG_CHECK(cudaMemsetAsync(e->table.slots, 0, (slots + 2) * sizeof(Slot), e->st));
 		if (e->flags & CMB200_FINGERPRINT) {
@@ -179,9 +202,12 @@ extern "C" cmb200_engine *cmb200_engine_create(const cmb200_config *cfg) {
 		// small per-chunk arrays are sized for a whole slice of a call (META_CAP chunks) so that
 		// they cross PCIe once, outside the page pipeline
 		const uint64_t M = cmb200_engine::META_CAP > B ? cmb200_engine::META_CAP : B;
-		ENG_CHECK(cudaMalloc(&e->d_addr, M * 16));
-		ENG_CHECK(cudaMalloc(&e->d_ts, M * 8));
-		ENG_CHECK(cudaMalloc(&e->d_valid, M));
+		// two copies: a host put stages the next call's arrays while the kernels of the previous
+		// one still read theirs (cmb200_put_batch_async)
+		e->meta_cap = M;
+		ENG_CHECK(cudaMalloc(&e->d_addr, 2 * M * 16));
+		ENG_CHECK(cudaMalloc(&e->d_ts, 2 * M * 8));
+		ENG_CHECK(cudaMalloc(&e->d_valid, 2 * M));
 		ENG_CHECK(cudaMalloc(&e->d_slot, B * 4));
 		ENG_CHECK(cudaMalloc(&e->d_vlen, B * 4));
 		ENG_CHECK(cudaMalloc(&e->d_lens, M * 4));
@@ -262,24 +288,60 @@ extern "C" int cmb200_sync(cmb200_engine *e) {
 
 // ---- put ---------------------------------------------------------------------------------
 
+// Adds the kernel times of asynchronous puts whose events have completed to the statistics;
+// wait = true blocks until every pending one has.
+static void harvest_pending(cmb200_engine *e, bool wait) {
+	while (e->pend_tail < e->pend_head) {
+		const int k = (int)(e->pend_tail % cmb200_engine::RING);
+		if (wait) cudaEventSynchronize(e->p1[k]);
+		else if (cudaEventQuery(e->p1[k]) != cudaSuccess) { (void)cudaGetLastError(); break; }
+		float ms = 0;
+		if (cudaEventElapsedTime(&ms, e->p0[k], e->p1[k]) == cudaSuccess) {
+			e->stats.encode_kernel_ns += (uint64_t)(ms * 1e6);
+			e->stats.encode_kernel_launches++;
+		}
+		e->pend_tail++;
+	}
+}
+
+// One slice (<= META_CAP chunks) of a put.  ticket == nullptr: returns when the chunks are stored.
+// ticket != nullptr (host pages only): returns as soon as the caller's arrays have crossed to the
+// device; the encode of the last sub-batch (and the copy of lens_out, which must then be
+// page-locked and stay valid) completes behind the ticket.
 static int put_slice(cmb200_engine *e, size_t n, const cmb200_addr *addr, const uint8_t *valid,
-    const uint8_t *pages, bool pages_on_dev, const uint64_t *ts, int32_t *lens_out) {
+    const uint8_t *pages, bool pages_on_dev, const uint64_t *ts, int32_t *lens_out, uint64_t *ticket) {
 	const size_t B = pages_on_dev ? e->max_batch : e->host_batch;
+	const bool deferred = ticket != nullptr;
 	// stage the small arrays in page-locked memory once; every copy below is then truly async
 	cmb200_addr *h_addr = (cmb200_addr *)e->h_meta;
 	uint64_t *h_ts = (uint64_t *)(e->h_meta + cmb200_engine::META_CAP * 16);
 	int32_t *h_lens = (int32_t *)(e->h_meta + cmb200_engine::META_CAP * 24);
 	uint8_t *h_valid = e->h_meta + cmb200_engine::META_CAP * 32;
+	harvest_pending(e, !deferred);
 	memcpy(h_addr, addr, n * 16);
 	if (ts) memcpy(h_ts, ts, n * 8);
 	if (valid) memcpy(h_valid, valid, n);
 	// The small arrays go over once, before the page pipeline starts: a small copy issued between
 	// two page copies would queue behind the next 256 MiB transfer in the copy engine and stall
-	// the kernels that wait for it.
-	CMB_CHECK(cudaMemcpyAsync(e->d_addr, h_addr, n * 16, cudaMemcpyHostToDevice, e->st));
-	if (valid) CMB_CHECK(cudaMemcpyAsync(e->d_valid, h_valid, n, cudaMemcpyHostToDevice, e->st));
-	if (ts) CMB_CHECK(cudaMemcpyAsync(e->d_ts, h_ts, n * 8, cudaMemcpyHostToDevice, e->st));
+	// the kernels that wait for it.  For host pages they travel on the copy stream into the copy of
+	// the arrays that the previous call is not using: on the compute stream they would wait for
+	// the previous call's last encode, and the page copies issued after them would wait with them
+	// in the copy engine's queue.
+	const int mb = pages_on_dev ? 0 : (int)(e->meta_pos++ & 1);
+	unsigned long long *d_addr = e->d_addr + (size_t)mb * e->meta_cap * 2;
+	unsigned long long *d_ts = e->d_ts + (size_t)mb * e->meta_cap;
+	uint8_t *d_valid = e->d_valid + (size_t)mb * e->meta_cap;
+	cudaStream_t ms = pages_on_dev ? e->st : e->copy;
+	if (!pages_on_dev) CMB_CHECK(cudaStreamWaitEvent(e->copy, e->meta_free[mb], 0));
+	CMB_CHECK(cudaMemcpyAsync(d_addr, h_addr, n * 16, cudaMemcpyHostToDevice, ms));
+	if (valid) CMB_CHECK(cudaMemcpyAsync(d_valid, h_valid, n, cudaMemcpyHostToDevice, ms));
+	if (ts) CMB_CHECK(cudaMemcpyAsync(d_ts, h_ts, n * 8, cudaMemcpyHostToDevice, ms));
+	if (!pages_on_dev) {
+		CMB_CHECK(cudaEventRecord(e->meta_done, e->copy));
+		CMB_CHECK(cudaStreamWaitEvent(e->st, e->meta_done, 0));
+	}
 	size_t nb = 0;
+	int last_buf = 0;
 	static const bool trace = getenv("CMB200_TRACE") != nullptr;
 	cudaEvent_t tr[4][16];
 	if (trace) for (int i = 0; i < 4; i++) for (int j = 0; j < 16; j++) cudaEventCreate(&tr[i][j]);
@@ -287,12 +349,14 @@ static int put_slice(cmb200_engine *e, size_t n, const cmb200_addr *addr, const 
 		// (splitting the last step into smaller ones to shorten the un-overlapped tail was tried:
 		// launches below ~4096 chunks run below PCIe rate, so the tail got longer, not shorter)
 		const uint32_t m = (uint32_t)((n - at < B) ? n - at : B);
-		const int buf = (int)(nb & 1);
+		const int buf = (int)(e->ring_pos & 1);
 		const uint8_t *d_in;
 		if (pages_on_dev) {
 			d_in = pages + at * e->bsize;
 		} else {
 			// land the pages in ring buffer `buf` once the kernels that last read it are done
+			e->ring_pos++;
+			last_buf = buf;
 			CMB_CHECK(cudaStreamWaitEvent(e->copy, e->consumed[buf], 0));
 			if (trace && nb < 16) cudaEventRecord(tr[0][nb], e->copy);
 			CMB_CHECK(cudaMemcpyAsync(e->d_pages[buf], pages + at * e->bsize, (size_t)m * e->bsize,
@@ -302,7 +366,7 @@ static int put_slice(cmb200_engine *e, size_t n, const cmb200_addr *addr, const 
 			CMB_CHECK(cudaStreamWaitEvent(e->st, e->landed[buf], 0));
 			d_in = e->d_pages[buf];
 		}
-		if (launch_upsert(e->table, e->d_addr + 2 * at, valid ? e->d_valid + at : nullptr, m, e->seq, e->seq_stride, e->d_slot, e->st)) return -1;
+		if (launch_upsert(e->table, d_addr + 2 * at, valid ? d_valid + at : nullptr, m, e->seq, e->seq_stride, e->d_slot, e->st)) return -1;
 		EncodeJob job{};
 		job.pages = d_in; job.page_stride = e->bsize; job.nbytes = e->bsize; job.n = m;
 		job.accel = (uint32_t)e->accel;
@@ -311,18 +375,38 @@ static int put_slice(cmb200_engine *e, size_t n, const cmb200_addr *addr, const 
 		job.fps = (e->flags & CMB200_FINGERPRINT) ? e->d_fps : nullptr;
 		job.work = e->d_work;
 		job.slot_idx = e->d_slot;
-		job.addr = e->d_addr + 2 * at;
-		job.ts = ts ? e->d_ts + at : nullptr;
+		job.addr = d_addr + 2 * at;
+		job.ts = ts ? d_ts + at : nullptr;
 		job.seq0 = e->seq; job.seq_stride = e->seq_stride;
 		job.table = e->table; job.arena = e->arena;
-		CMB_CHECK(cudaEventRecord(e->t0[nb % e->RING], e->st));
+		cudaEvent_t ev0, ev1;
+		if (deferred) {
+			if (e->pend_head - e->pend_tail >= (uint64_t)cmb200_engine::RING) harvest_pending(e, true);
+			ev0 = e->p0[e->pend_head % cmb200_engine::RING]; ev1 = e->p1[e->pend_head % cmb200_engine::RING];
+			e->pend_head++;
+		} else {
+			ev0 = e->t0[nb % e->RING]; ev1 = e->t1[nb % e->RING];
+		}
+		CMB_CHECK(cudaEventRecord(ev0, e->st));
 		if (trace && nb < 16) cudaEventRecord(tr[2][nb], e->st);
 		if (launch_encode(job, e->st)) return -1;
 		if (trace && nb < 16) cudaEventRecord(tr[3][nb], e->st);
-		CMB_CHECK(cudaEventRecord(e->t1[nb % e->RING], e->st));
+		CMB_CHECK(cudaEventRecord(ev1, e->st));
 		if (!pages_on_dev) CMB_CHECK(cudaEventRecord(e->consumed[buf], e->st));
 		e->seq += (unsigned long long)m * e->seq_stride;
 		e->stats.kernel_launches += 2;
+	}
+	e->stats.put_chunks += n;
+	if (!pages_on_dev) CMB_CHECK(cudaEventRecord(e->meta_free[mb], e->st));
+	if (deferred) {
+		if (lens_out) CMB_CHECK(cudaMemcpyAsync(lens_out, e->d_lens, n * 4, cudaMemcpyDeviceToHost, e->st));
+		CMB_CHECK(cudaEventRecord(e->ticket_ev[e->tickets % cmb200_engine::TICKETS], e->st));
+		*ticket = ++e->tickets;
+		// the caller may reuse addr / valid / ts / pages once they have crossed
+		CMB_CHECK(cudaEventSynchronize(e->meta_done));
+		if (nb) CMB_CHECK(cudaEventSynchronize(e->landed[last_buf]));
+		harvest_pending(e, false);
+		return 0;
 	}
 	if (lens_out) CMB_CHECK(cudaMemcpyAsync(h_lens, e->d_lens, n * 4, cudaMemcpyDeviceToHost, e->st));
 	CMB_CHECK(cudaStreamSynchronize(e->st));
@@ -342,29 +426,49 @@ static int put_slice(cmb200_engine *e, size_t n, const cmb200_addr *addr, const 
 		e->stats.encode_kernel_ns += (uint64_t)(ms * 1e6);
 		e->stats.encode_kernel_launches++;
 	}
-	e->stats.put_chunks += n;
 	return 0;
 }
 
 static int put_impl(cmb200_engine *e, size_t n, const cmb200_addr *addr, const uint8_t *valid,
-    const uint8_t *pages, bool pages_on_dev, const uint64_t *ts, int32_t *lens_out) {
+    const uint8_t *pages, bool pages_on_dev, const uint64_t *ts, int32_t *lens_out, uint64_t *ticket) {
 	std::lock_guard<std::mutex> g(e->mu);
 	CMB_CHECK(cudaSetDevice(e->device));
+	if (ticket) *ticket = e->tickets;       // nothing to wait for unless the last slice is deferred
 	for (size_t at = 0; at < n; at += cmb200_engine::META_CAP) {
 		size_t m = n - at < cmb200_engine::META_CAP ? n - at : cmb200_engine::META_CAP;
+		const bool last = at + m == n;
 		if (put_slice(e, m, addr + at, valid ? valid + at : nullptr, pages + at * e->bsize, pages_on_dev,
-			ts ? ts + at : nullptr, lens_out ? lens_out + at : nullptr)) return -1;
+			ts ? ts + at : nullptr, lens_out ? lens_out + at : nullptr, last ? ticket : nullptr)) return -1;
 	}
 	return 0;
 }
 
 extern "C" int cmb200_put_batch(cmb200_engine *e, size_t n, const cmb200_addr *addr, const uint8_t *valid,
     const void *pages_host, const uint64_t *ts, int32_t *lens_out) {
-	return put_impl(e, n, addr, valid, (const uint8_t *)pages_host, false, ts, lens_out);
+	return put_impl(e, n, addr, valid, (const uint8_t *)pages_host, false, ts, lens_out, nullptr);
+}
+extern "C" int cmb200_put_batch_async(cmb200_engine *e, size_t n, const cmb200_addr *addr, const uint8_t *valid,
+    const void *pages_host, const uint64_t *ts, int32_t *lens_out, uint64_t *ticket) {
+	uint64_t t = 0;
+	const int rc = put_impl(e, n, addr, valid, (const uint8_t *)pages_host, false, ts, lens_out, &t);
+	if (ticket) *ticket = t;
+	return rc;
+}
+extern "C" int cmb200_wait(cmb200_engine *e, uint64_t ticket) {
+	cudaEvent_t ev = nullptr;
+	{
+		std::lock_guard<std::mutex> g(e->mu);
+		if (ticket == 0 || ticket > e->tickets) return 0;
+		// a ticket whose event has been recorded again waits for the later put: the stream is in order
+		ev = e->ticket_ev[(ticket - 1) % cmb200_engine::TICKETS];
+		if (cudaSetDevice(e->device) != cudaSuccess) return -1;
+	}
+	CMB_CHECK(cudaEventSynchronize(ev));
+	return 0;
 }
 extern "C" int cmb200_put_batch_dev(cmb200_engine *e, size_t n, const cmb200_addr *addr, const uint8_t *valid,
     const void *pages_dev, const uint64_t *ts, int32_t *lens_out) {
-	return put_impl(e, n, addr, valid, (const uint8_t *)pages_dev, true, ts, lens_out);
+	return put_impl(e, n, addr, valid, (const uint8_t *)pages_dev, true, ts, lens_out, nullptr);
 }
 
 // ---- get ---------------------------------------------------------------------------------
@@ -520,6 +624,7 @@ extern "C" int cmb200_get_stats(cmb200_engine *e, cmb200_stats *out) {
 	std::lock_guard<std::mutex> g(e->mu);
 	unsigned long long c[8];
 	if (read_counters(e, c)) return -1;
+	harvest_pending(e, true);
 	*out = e->stats;
 	out->entries = c[0]; out->tombstones = c[1]; out->arena_used = c[2]; out->arena_garbage = c[3];
 	out->dropped_puts = c[4]; out->remote_entries = c[5];

@@ -57,6 +57,25 @@ void cachemap_put_batch_dev(struct cachemap *cm, uint64_t n, const uint64_t *off
 void cachemap_get_batch_dev(struct cachemap *cm, uint64_t n, const uint64_t *offset,
     const uint64_t *nhid_small, const uint32_t *genid, void *pages_out_dev, uint8_t *hit_out);
 
+/*
+ * ---- request-range calls: the page loops of the FUSE callbacks as one call -----------------
+ * edgefs_read (edgefs.c:1159-1178) walks the pages of a request with cachemap_get and gives up at
+ * the first miss; its miss path and edgefs_write (edgefs.c:1183-1195, 1216-1228) put every page
+ * of the request.  These two calls do the same for a whole request at once — the gets as ONE GPU
+ * batch — after applying the gate of edgefs.c:192-203 (both ends page-aligned, see
+ * edgefs_glue.h).
+ *
+ * cachemap_read_range: returns 1 and fills out_buf[0..size) when the range passes the gate and
+ * every page hits; returns 0 otherwise (out_buf contents are then unspecified, as after the
+ * reference's partial loop).  requests / hits advance exactly as the reference's loop advances
+ * them: pages after the first miss are not counted.  size 0 returns 1 (the loop body never runs).
+ * cachemap_write_range: puts every page of the range if it passes the gate, else does nothing.
+ */
+int cachemap_read_range(struct cachemap *cm, uint64_t nhid_small, uint32_t genid, uint64_t off,
+    size_t size, void *out_buf);
+void cachemap_write_range(struct cachemap *cm, uint64_t nhid_small, uint32_t genid, uint64_t off,
+    size_t size, const void *data);
+
 /* requests / hits counters (cachemap.c:176,181) and the engine under the map. */
 void cachemap_get_counters(struct cachemap *cm, uint64_t *requests, uint64_t *hits);
 struct cmb200_engine *cachemap_engine(struct cachemap *cm);

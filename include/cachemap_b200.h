@@ -78,6 +78,18 @@ int cmb200_put_batch(cmb200_engine *e, size_t n, const cmb200_addr *addr, const 
 int cmb200_put_batch_dev(cmb200_engine *e, size_t n, const cmb200_addr *addr, const uint8_t *valid,
     const void *pages_dev, const uint64_t *ts, int32_t *lens_out);
 
+/* Write-behind form of cmb200_put_batch, the batch analogue of cachemap_put_async
+ * (cachemap/cachemap.c:199-216): returns as soon as addr / valid / pages_host / ts have crossed to
+ * the device and may be reused by the caller, like the borrowed page of cachemap_put; the encode of
+ * the last sub-batch completes behind *ticket.  Every later call on this engine (gets included)
+ * is ordered after the put, so waiting is needed only before reading lens_out, which must then be
+ * page-locked (cmb200_host_alloc) and stay valid until cmb200_wait(ticket) has returned.
+ * Submitting batch k+1 before waiting for batch k overlaps its host-to-device copy with the tail
+ * of batch k's encode. */
+int cmb200_put_batch_async(cmb200_engine *e, size_t n, const cmb200_addr *addr, const uint8_t *valid,
+    const void *pages_host, const uint64_t *ts, int32_t *lens_out, uint64_t *ticket);
+int cmb200_wait(cmb200_engine *e, uint64_t ticket);
+
 /* filemap_get for n requests (cachemap/filemap.c:217-262).  status_out[i] is one of CMB200_*;
  * pages_out receives 1<<pshift bytes per request (untouched for non-hits). */
 int cmb200_get_batch(cmb200_engine *e, size_t n, const cmb200_addr *addr, const uint8_t *valid,

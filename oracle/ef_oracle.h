@@ -69,4 +69,9 @@ void ef_fingerprint128(const uint8_t *data, size_t n, uint64_t out[2]);
 #ifdef __cplusplus
 }
 #endif
+/* Caller-side gate and object id (edgefs.c:192-212,1911). */
+int ef_cache_check(int have_cache, int pshift, uint64_t off, uint64_t size, uint64_t *page_size_out,
+    uint64_t *aligned_off_out);
+uint64_t ef_build_nhid(const char *name, const char *bucket_path);
+
 #endif

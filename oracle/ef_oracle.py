@@ -49,6 +49,10 @@ def lib() -> C.CDLL:
         L.ef_lz4_bound.argtypes = [C.c_int]
         L.ef_record_prefix.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         L.ef_fingerprint128.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+        L.ef_cache_check.restype = C.c_int
+        L.ef_cache_check.argtypes = [C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
+        L.ef_build_nhid.restype = C.c_uint64
+        L.ef_build_nhid.argtypes = [C.c_char_p, C.c_char_p]
         L.ef_cpu_bench_codec.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int,
                                          C.c_int, C.c_int, C.c_void_p]
         L.ef_cpu_bench_store.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -86,6 +90,8 @@ def ref():
 
 
 def _u8(a) -> np.ndarray:
+    if isinstance(a, (bytes, bytearray, memoryview)):
+        a = np.frombuffer(a, dtype=np.uint8)
     a = np.ascontiguousarray(a, dtype=np.uint8)
     return a
 
@@ -93,6 +99,18 @@ def _u8(a) -> np.ndarray:
 def fnv1a64(data: bytes) -> int:
     buf = (C.c_char * max(len(data), 1)).from_buffer_copy(data or b"\0")
     return int(lib().ef_fnv1a64(buf, len(data)))
+
+
+def cache_check(have_cache: bool, pshift: int, off: int, size: int):
+    """edgefs.c:192-203 -> (do_cache, page_size, aligned_off)."""
+    ps, ao = C.c_uint64(), C.c_uint64()
+    ok = lib().ef_cache_check(int(have_cache), pshift, off, size, C.byref(ps), C.byref(ao))
+    return bool(ok), ps.value, ao.value
+
+
+def build_nhid(name: bytes, bucket_path: bytes) -> int:
+    """edgefs.c:205-212 with bhid_small = FNV(url path) (edgefs.c:1911)."""
+    return int(lib().ef_build_nhid(name, bucket_path))
 
 
 def addr_compose(offset: int, nhid: int, genid: int, pshift: int):
@@ -201,6 +219,33 @@ class StoreModel:
 
     def unset(self, u: int, l: int) -> None:
         self.rec.pop(addr_key(u, l), None)
+
+    def read_range(self, nhid: int, genid: int, off: int, size: int):
+        """The cache part of edgefs_read (edgefs.c:1150-1178): gate, then get page after page
+        until the first miss.  -> bytes or None."""
+        do_cache, page_size, aligned = cache_check(True, self.pshift, off, size)
+        if not do_cache:
+            return None
+        out = b""
+        i = aligned
+        while i < off + size:
+            page = self.get(i, nhid, genid)
+            if page is None:
+                return None
+            out += bytes(page)
+            i += page_size
+        return out
+
+    def write_range(self, nhid: int, genid: int, off: int, data: bytes) -> None:
+        """The put loop of edgefs.c:1183-1195 / 1216-1228."""
+        do_cache, page_size, aligned = cache_check(True, self.pshift, off, len(data))
+        if not do_cache:
+            return
+        i, b = aligned, 0
+        while i < off + len(data):
+            self.put(i, nhid, genid, data[b:b + page_size])
+            i += page_size
+            b += page_size
 
     def entries(self) -> int:
         return len(self.rec)

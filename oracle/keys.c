@@ -54,3 +54,24 @@ ef_record_prefix(const ef_addr_t *a, int32_t compressed_length, uint8_t out[24])
 	memcpy(out + 8, &a->l, 8);
 	memcpy(out + 16, &compressed_length, 4);
 }
+
+/* edgefs.c:192-203 (cachemap_cache_check): cache only requests whose two ends are page-aligned.
+ * The reference reads the globals cachemap_pshift / cachemap_obj; they are arguments here. */
+int
+ef_cache_check(int have_cache, int pshift, uint64_t off, uint64_t size, uint64_t *page_size_out,
+    uint64_t *aligned_off_out)
+{
+	uint64_t page_size = 1ULL << pshift;
+	uint64_t unaligned_start = off & (page_size - 1);
+	uint64_t unaligned_end = (off + size) & (page_size - 1);
+	*page_size_out = page_size;
+	*aligned_off_out = off - unaligned_start;
+	return have_cache && !unaligned_start && !unaligned_end;
+}
+
+/* edgefs.c:205-212 (cachemap_build_nhid) with bhid_small from edgefs.c:1911 (FNV of the url path) */
+uint64_t
+ef_build_nhid(const char *name, const char *bucket_path)
+{
+	return ef_fnv1a64(name, strlen(name)) ^ ef_fnv1a64(bucket_path, strlen(bucket_path));
+}

@@ -76,3 +76,39 @@ def test_host_stream_generator(E):
     assert cids.max() == distinct - 1
     cids0, d0 = E.gen_stream_ids(1000, 0.0)
     assert d0 == 1000 and (cids0 == np.arange(1000)).all()
+
+
+def test_edgefs_glue_header_matches_oracle(tmp_path, oracle):
+    """include/edgefs_glue.h (the gate and the object id that edgefs.c computes
+    before it calls the cache, edgefs.c:192-212,1911) against the oracle restatement, plus known
+    answers taken with the reference's own FNV_hash."""
+    import subprocess
+    so = tmp_path / "glue_shim.so"
+    subprocess.check_call(["gcc", "-std=gnu99", "-O2", "-shared", "-fPIC", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "c", "glue_shim.c"), "-o", str(so)])
+    L = ctypes.CDLL(str(so))
+    L.shim_cache_check.restype = ctypes.c_int
+    L.shim_cache_check.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64,
+                                   ctypes.c_void_p, ctypes.c_void_p]
+    L.shim_build_nhid.restype = ctypes.c_uint64
+    L.shim_build_nhid.argtypes = [ctypes.c_char_p, ctypes.c_char_p]
+    rng = np.random.default_rng(5)
+    for pshift in range(12, 18):
+        page = 1 << pshift
+        cases = [(0, 0), (0, page), (page, 2 * page), (1, page), (page, page - 1), (page - 1, 1),
+                 (3 * page, 131072), ((1 << 60) + page, page), (2**64 - page, page)]
+        cases += [(int(rng.integers(0, 1 << 40)) & ~(page - 1 if rng.random() < 0.5 else 0),
+                   int(rng.integers(0, 1 << 20)) & ~(page - 1 if rng.random() < 0.5 else 0)) for _ in range(200)]
+        for have in (0, 1):
+            for off, size in cases:
+                ps, ao = ctypes.c_uint64(), ctypes.c_uint64()
+                got = L.shim_cache_check(have, pshift, off, size, ctypes.byref(ps), ctypes.byref(ao))
+                assert (bool(got), ps.value, ao.value) == oracle.cache_check(bool(have), pshift, off, size)
+    # FNV_hash("/bk1") = 0x1e400c9ca688f534, FNV_hash("") = offset basis (reference objects, SURVEY §8c)
+    assert L.shim_build_nhid(b"", b"/bk1") == 0xcbf29ce484222325 ^ 0x1e400c9ca688f534
+    assert L.shim_build_nhid(b"a", b"") == 0xaf63dc4c8601ec8c ^ 0xcbf29ce484222325
+    for _ in range(100):
+        name = bytes(rng.integers(1, 256, int(rng.integers(0, 64)), dtype=np.uint8))
+        path = b"/" + bytes(rng.integers(1, 256, int(rng.integers(0, 200)), dtype=np.uint8))
+        assert L.shim_build_nhid(name, path) == oracle.build_nhid(name, path) \
+            == oracle.fnv1a64(name) ^ oracle.fnv1a64(path)

@@ -365,3 +365,95 @@ print("direct ok", used)
     env = dict(os.environ, CMB200_SEG_KB="320")
     out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0 and "direct ok" in out.stdout, out.stdout + out.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pshift", [12, 16])
+def test_request_ranges_follow_the_fuse_loops(E, gpu, oracle, tmp_path, pshift):
+    """cachemap_read_range / _write_range against the page loops of edgefs_read / edgefs_write
+    (edgefs.c:1150-1195, 1216-1228) replayed on the store model: same bytes, same hit/miss answer
+    per request, same requests / hits counters (pages after the first miss are never asked for)."""
+    import datagen
+    page = 1 << pshift
+    cm = E.Cachemap(str(tmp_path), 4096, 12, pshift)
+    model = oracle.StoreModel(pshift, 12)
+    rng = np.random.default_rng(pshift)
+    nhids = [oracle.build_nhid(b"obj%d" % i, b"/bk1") for i in range(3)]
+    span = 64                                           # pages per object that the trace touches
+    for step in range(400):
+        nh = nhids[int(rng.integers(0, 3))]
+        first = int(rng.integers(0, span))
+        npages = int(rng.integers(1, min(32, 131072 // page) + 1))      # max_write 131072 (edgefs.c:1366)
+        off, size = first * page, npages * page
+        kind = rng.random()
+        if kind < 0.08:                                 # unaligned requests bypass the cache
+            off += int(rng.integers(1, page))
+        elif kind < 0.12:
+            size -= int(rng.integers(1, page))
+        elif kind < 0.15:
+            off = ((1 << 44) - 1) * page if pshift == 16 else off     # last valid page, then invalid ones
+        if rng.random() < 0.45:
+            data = b"".join(datagen.make_page("RTZMPAXS"[int(rng.integers(0, 8))], page, step * 40 + j).tobytes()
+                            for j in range((size + page - 1) // page))[:size]
+            cm.write_range(nh, 0, off, data)
+            model.write_range(nh, 0, off, data)
+        else:
+            got = cm.read_range(nh, 0, off, size)
+            want = model.read_range(nh, 0, off, size)
+            assert got == want, (step, off, size)
+        assert cm.counters() == (model.requests, model.hits), step
+    assert cm.read_range(nhids[0], 0, 0, 0) == b""      # empty request: the loop body never runs
+    cm.free()
+
+
+def test_async_put_batches_overlap_and_stay_ordered(E, gpu, oracle):
+    """cmb200_put_batch_async returns once the host arrays have crossed: the same host buffer is
+    refilled for the next batch straight away, the stored lengths arrive behind the ticket, and
+    later calls (rewrites of the same keys, gets) are ordered after the pending encode."""
+    n, rounds = 1500, 5
+    eng = E.Engine(pshift=16, accel=12, capacity=16384, arena_bytes=1 << 30, max_batch=512, flags=E.FINGERPRINT)
+    ct = np.ctypeslib.ctypes
+    hp = E.lib().cmb200_host_alloc(n * 65536)
+    pages = np.ctypeslib.as_array((ct.c_uint8 * (n * 65536)).from_address(hp)).reshape(n, 65536)
+    lens_pin = []
+    for _ in range(2):
+        p = E.lib().cmb200_host_alloc(n * 4)
+        lens_pin.append((p, np.ctypeslib.as_array((ct.c_int32 * n).from_address(p))))
+    src = [np.stack([E.gen_chunk_host(100 + r, c, 65536) for c in range(n)]) for r in range(rounds)]
+    sample = list(range(0, n, 61))
+    u = np.full(n, 5, dtype=np.uint64)
+    tickets = []
+
+    def check_lens(r):
+        eng.wait(tickets[r])
+        got = lens_pin[r & 1][1]
+        assert (got > 0).all(), r
+        for k in sample:
+            assert int(got[k]) == len(oracle.lz4_encode(src[r][k], 12)), (r, k)
+
+    for r in range(rounds):
+        l = np.arange(n, dtype=np.uint64) + np.uint64((r % 2) * (n // 2))      # half the keys get rewritten
+        if r >= 2:
+            check_lens(r - 2)                                                   # frees lens_pin[r & 1]
+        pages[:] = src[r]                                                       # host buffer reused at once
+        tickets.append(eng.put_async(u, l, pages, lens=lens_pin[r & 1][0]))
+    check_lens(rounds - 2)
+    check_lens(rounds - 1)
+    newest = {}
+    for r in range(rounds):
+        for k in range(n):
+            newest[k + (r % 2) * (n // 2)] = (r, k)
+    keys = np.array(sorted(newest), dtype=np.uint64)
+    out, status = eng.get(np.full(len(keys), 5, dtype=np.uint64), keys)
+    assert (status == E.HIT).all()
+    for i, key in enumerate(keys):
+        r, k = newest[int(key)]
+        assert (out[i] == src[r][k]).all(), (int(key), r, k)
+    assert eng.entries() == len(keys)
+    eng.wait(0)
+    eng.wait(tickets[0])                                                        # stale tickets return at once
+    st = eng.stats()
+    assert st["put_chunks"] == n * rounds and st["dropped_puts"] == 0
+    for p in [hp] + [x[0] for x in lens_pin]:
+        E.lib().cmb200_host_free(p)
+    eng.close()
