@@ -19,7 +19,7 @@ EXPORTED_SYMBOLS = [
     "cachemap_create", "cachemap_free", "cachemap_get", "cachemap_put", "cachemap_put_async",
     "cachemap_print_stats", "cachemap_put_batch", "cachemap_get_batch", "cachemap_put_batch_dev",
     "cachemap_get_batch_dev", "cachemap_get_counters", "cachemap_engine",
-    "cachemap_read_range", "cachemap_write_range",
+    "cachemap_read_range", "cachemap_write_range", "cachemap_checkpoint",
     # filemap.h — reference cachemap/filemap.h:19-29
     "filemap_create", "filemap_free", "filemap_set", "filemap_unset", "filemap_get",
     "filemap_get_rand", "filemap_entries",
@@ -30,7 +30,7 @@ EXPORTED_SYMBOLS = [
     "cmb200_put_batch", "cmb200_put_batch_dev", "cmb200_put_batch_async", "cmb200_wait", "cmb200_get_batch", "cmb200_get_batch_dev",
     "cmb200_unset_batch", "cmb200_entries", "cmb200_sample", "cmb200_read_records",
     "cmb200_read_fingerprints", "cmb200_get_stats", "cmb200_compose_keys",
-    "cmb200_set_stream_order", "cmb200_import_remote", "cmb200_locate_batch",
+    "cmb200_set_stream_order", "cmb200_import_remote", "cmb200_locate_batch", "cmb200_save", "cmb200_load",
     "cmb200_lz4_encode_batch", "cmb200_lz4_decode_batch", "cmb200_fingerprint_batch", "cmb200_fingerprint_dev",
     "cmb200_gen_chunk_host", "cmb200_gen_chunks_dev", "cmb200_gen_stream_ids", "cmb200_gen_addr",
 ]
@@ -79,6 +79,7 @@ def lib() -> C.CDLL:
         "cachemap_get_batch_dev": (None, [vp, u64, vp, vp, vp, vp, vp]),
         "cachemap_get_counters": (None, [vp, vp, vp]),
         "cachemap_engine": (vp, [vp]),
+        "cachemap_checkpoint": (i32, [vp]),
         "cachemap_read_range": (i32, [vp, u64, u32, u64, sz, vp]),
         "cachemap_write_range": (None, [vp, u64, u32, u64, sz, vp]),
         "filemap_create": (vp, [C.c_char_p, u64, i32, i32]),
@@ -104,6 +105,8 @@ def lib() -> C.CDLL:
         "cmb200_put_batch_dev": (i32, [vp, sz, vp, vp, vp, vp, vp]),
         "cmb200_put_batch_async": (i32, [vp, sz, vp, vp, vp, vp, vp, vp]),
         "cmb200_wait": (i32, [vp, u64]),
+        "cmb200_save": (i32, [vp, C.c_char_p, vp]),
+        "cmb200_load": (i32, [vp, C.c_char_p, vp]),
         "cmb200_get_batch": (i32, [vp, sz, vp, vp, vp, vp]),
         "cmb200_get_batch_dev": (i32, [vp, sz, vp, vp, vp, vp]),
         "cmb200_unset_batch": (i32, [vp, sz, vp]),
@@ -338,6 +341,16 @@ class Engine:
                "cmb200_read_fingerprints")
         return fps, ok
 
+    def save(self, path: str) -> int:
+        n = C.c_uint64(0)
+        _check(lib().cmb200_save(self.h, path.encode(), C.byref(n)), "cmb200_save")
+        return n.value
+
+    def load(self, path: str) -> int:
+        n = C.c_uint64(0)
+        _check(lib().cmb200_load(self.h, path.encode(), C.byref(n)), "cmb200_load")
+        return n.value
+
     def set_stream_order(self, next_seq: int, stride: int):
         _check(lib().cmb200_set_stream_order(self.h, next_seq, stride), "cmb200_set_stream_order")
 
@@ -452,6 +465,9 @@ class Cachemap:
         """The put loop of edgefs_read's miss path / edgefs_write (edgefs.c:1183-1195,1216-1228)."""
         data = np.ascontiguousarray(np.frombuffer(data, dtype=np.uint8) if isinstance(data, (bytes, bytearray)) else data)
         lib().cachemap_write_range(self.h, nhid, genid, off, data.size, _ptr(data))
+
+    def checkpoint(self) -> int:
+        return int(lib().cachemap_checkpoint(self.h))
 
     def counters(self):
         rq, ht = C.c_uint64(), C.c_uint64()

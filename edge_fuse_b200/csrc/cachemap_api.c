@@ -27,6 +27,7 @@
 #include <string.h>
 #include <sys/stat.h>
 #include <time.h>
+#include <unistd.h>
 
 #include "../../include/cachemap.h"
 #include "../../include/cachemap_b200.h"
@@ -79,7 +80,20 @@ struct filemap {
 	uint64_t wb_n, wb_head, wb_tail;
 	pthread_t wb_thread;
 	int wb_started, wb_stop;
+	/* persistence: <destdir>/cachemap_b200.snap (cmb200_save / cmb200_load) */
+	int persist;
+	long checkpoint_sec;    /* > 0: the flusher saves a snapshot this often when puts have arrived */
+	uint64_t puts_seen, puts_saved;
+	pthread_mutex_t snap_mu;
 };
+
+#define SNAPSHOT_NAME "cachemap_b200.snap"
+
+static int
+filemap_snapshot_path(struct filemap *m, char *out, size_t cap)
+{
+	return snprintf(out, cap, "%s/%s", m->destdir, SNAPSHOT_NAME) < (int)cap;
+}
 
 static long
 env_long(const char *name, long dflt)
@@ -129,6 +143,16 @@ filemap_engine_ready(struct filemap *m)
 			}
 			__atomic_store_n(&m->init_state, -1, __ATOMIC_RELEASE);
 		} else {
+			/* what the cache directory holds from an earlier run comes back first: the reference's
+			 * store is persistent (LMDB files under destdir, filemap.c:57,71-72) */
+			m->persist = (int)env_long("CMB200_PERSIST", 1);
+			m->checkpoint_sec = env_long("CMB200_CHECKPOINT_SEC", 0);
+			char snap[2200];
+			if (m->persist && filemap_snapshot_path(m, snap, sizeof(snap)) && access(snap, R_OK) == 0) {
+				uint64_t got = 0;
+				if (cmb200_load(m->eng, snap, &got) != 0)
+					fprintf(stderr, "cachemap_b200: %s ignored: %s\n", snap, cmb200_last_error());
+			}
 			/* the flusher starts here, i.e. in the process that actually caches (after any fork) */
 			if (m->wb_n && pthread_create(&m->wb_thread, NULL, filemap_flusher, m) == 0)
 				m->wb_started = 1;
@@ -165,7 +189,28 @@ filemap_create(char *destdir, uint64_t n, int compress_accel, int pshift)
 	pthread_cond_init(&m->wb_space, NULL);
 	pthread_cond_init(&m->wb_work, NULL);
 	pthread_cond_init(&m->wb_idle, NULL);
+	pthread_mutex_init(&m->snap_mu, NULL);
 	return m;
+}
+
+/* Saves the store to <destdir>/cachemap_b200.snap.  0 = saved, -1 = not (disabled, engine never
+ * started, or I/O error). */
+static int
+filemap_save(struct filemap *m)
+{
+	char snap[2200];
+	if (__atomic_load_n(&m->init_state, __ATOMIC_ACQUIRE) != 1 || !m->persist ||
+	    !filemap_snapshot_path(m, snap, sizeof(snap)))
+		return -1;
+	pthread_mutex_lock(&m->snap_mu);
+	uint64_t seen = __atomic_load_n(&m->puts_seen, __ATOMIC_RELAXED);
+	int rc = cmb200_save(m->eng, snap, NULL);
+	if (rc == 0)
+		m->puts_saved = seen;
+	else
+		fprintf(stderr, "cachemap_b200: snapshot not written: %s\n", cmb200_last_error());
+	pthread_mutex_unlock(&m->snap_mu);
+	return rc;
 }
 
 /* Waits until every page accepted so far is in the GPU store. */
@@ -192,6 +237,7 @@ filemap_free(struct filemap *m)
 		pthread_mutex_unlock(&m->wb_mu);
 		pthread_join(m->wb_thread, NULL);      /* drains the ring first */
 	}
+	filemap_save(m);                                /* the cache directory outlives the process */
 	if (m->wb_pages)
 		cmb200_host_free(m->wb_pages);
 	free(m->wb_slot);
@@ -199,6 +245,7 @@ filemap_free(struct filemap *m)
 		cmb200_host_free(m->h_stage);
 	if (m->eng)
 		cmb200_engine_destroy(m->eng);
+	pthread_mutex_destroy(&m->snap_mu);
 	pthread_mutex_destroy(&m->init_mu);
 	pthread_mutex_destroy(&m->q_mu);
 	pthread_cond_destroy(&m->q_cv);
@@ -270,6 +317,7 @@ filemap_flusher(void *arg)
 	struct filemap *m = arg;
 	cmb200_addr *addr = malloc(FLUSH_MAX * sizeof(cmb200_addr));
 	uint64_t *ts = malloc(FLUSH_MAX * sizeof(uint64_t));
+	time_t last_save = time(NULL);
 	pthread_mutex_lock(&m->wb_mu);
 	for (;;) {
 		uint64_t count = 0;
@@ -279,7 +327,22 @@ filemap_flusher(void *arg)
 		if (count == 0) {
 			if (m->wb_stop && m->wb_tail == m->wb_head)
 				break;
-			pthread_cond_wait(&m->wb_work, &m->wb_mu);
+			if (m->checkpoint_sec > 0 && m->persist) {
+				struct timespec now, until;
+				clock_gettime(CLOCK_REALTIME, &now);
+				if (m->puts_seen != m->puts_saved && now.tv_sec - last_save >= m->checkpoint_sec) {
+					pthread_mutex_unlock(&m->wb_mu);
+					filemap_save(m);
+					pthread_mutex_lock(&m->wb_mu);
+					last_save = now.tv_sec;
+					continue;
+				}
+				until = now;
+				until.tv_sec += 1;
+				pthread_cond_timedwait(&m->wb_work, &m->wb_mu, &until);
+			} else {
+				pthread_cond_wait(&m->wb_work, &m->wb_mu);
+			}
 			continue;
 		}
 		for (uint64_t i = 0; i < count; i++) {
@@ -300,6 +363,7 @@ filemap_flusher(void *arg)
 		}
 
 		pthread_mutex_lock(&m->wb_mu);
+		__atomic_fetch_add(&m->puts_seen, count, __ATOMIC_RELAXED);
 		for (uint64_t i = 0; i < count; i++)
 			m->wb_slot[(m->wb_tail + i) % m->wb_n].state = WB_FREE;
 		m->wb_tail += count;
@@ -428,6 +492,7 @@ filemap_set(struct filemap *m, uint128_t *key, void *value, uint64_t attr)
 	if (!m->wb_n) {                         /* write-behind disabled: one synchronous GPU put */
 		filemap_make_room(m, 1);
 		cmb200_put_batch(m->eng, 1, &a, NULL, value, &attr, NULL);
+		__atomic_fetch_add(&m->puts_seen, 1, __ATOMIC_RELAXED);
 		return;
 	}
 	pthread_mutex_lock(&m->wb_mu);
@@ -654,6 +719,7 @@ put_batch_common(struct cachemap *cm, uint64_t n, const uint64_t *offset, const 
 		return;
 	filemap_drain(cm->pages);               /* earlier single puts land first */
 	filemap_make_room(cm->pages, n);
+	__atomic_fetch_add(&cm->pages->puts_seen, n, __ATOMIC_RELAXED);
 	if (on_dev)
 		cmb200_put_batch_dev(cm->pages->eng, (size_t)n, bk.addr, bk.valid, pages, bk.ts, NULL);
 	else {
@@ -807,6 +873,15 @@ cachemap_write_range(struct cachemap *cm, uint64_t nhid_small, uint32_t genid, u
 	 * edgefs.c:1186-1190 / 1219-1223 already hands the GPU one batch */
 	for (uint64_t i = 0; i < ((uint64_t)size >> pshift); i++)
 		cachemap_put(cm, off + (i << pshift), nhid_small, genid, (const uint8_t *)data + (i << pshift));
+}
+
+int
+cachemap_checkpoint(struct cachemap *cm)
+{
+	if (!filemap_engine_ready(cm->pages))
+		return -1;
+	filemap_drain(cm->pages);
+	return filemap_save(cm->pages);
 }
 
 void

@@ -8,7 +8,9 @@
 // A put batch is: H2D copy (copy stream)  ->  k_upsert  ->  k_encode (fingerprint + LZ4 + arena
 // commit + table publish), sub-batch k+1's copy overlapping sub-batch k's kernels.
 // A get batch is: k_lookup -> k_decode -> D2H copy.
+#include <algorithm>
 #include <mutex>
+#include <string>
 #include <new>
 #include <stdio.h>
 #include <stdlib.h>
@@ -693,14 +695,153 @@ extern "C" int cmb200_read_fingerprints(cmb200_engine *e, size_t n, const cmb200
 	return 0;
 }
 
-// ---- kernel-level entry points -------------------------------------------------------------
-
 struct DevBuf {
 	void *p = nullptr;
 	~DevBuf() { if (p) cudaFree(p); }
 	int alloc(size_t bytes) { CMB_CHECK(cudaMalloc(&p, bytes + 256)); return 0; }
 	template <class T> T *as() { return (T *)p; }
 };
+
+// ---- snapshot: persistence of the cache directory ---------------------------
+//
+// The reference's store is persistent because it IS a set of LMDB files under <cachedir>
+// (filemap.c:57,71-72).  Here the store lives in HBM, so it is saved to / restored from one file of
+// records, each exactly the LMDB value of the reference (24-byte data_prefix + payload,
+// filemap.c:140-147) preceded by {ts (the LMDB attribute), length, fingerprint}:
+//
+//   header   "CMB200S1" | u32 version=1 | u32 pshift | u64 records | u64 payload bytes | u32 flags | pad to 64
+//   record   u64 ts | u64 fp_hi | u64 fp_lo | u32 len | u32 0 | len bytes {u, l, compressed_length, pad, payload} | pad to 16
+//
+// It does not depend on the table geometry or the arena layout, so a snapshot loads into an engine
+// of any capacity (records that do not fit are dropped like puts into a full store).
+struct SnapHeader {
+	char magic[8];
+	uint32_t version, pshift;
+	uint64_t records, bytes;
+	uint32_t flags, pad[7];
+};
+static_assert(sizeof(SnapHeader) == 64, "snapshot header");
+struct SnapRecord { uint64_t ts, fp_hi, fp_lo; uint32_t len, zero; };
+static_assert(sizeof(SnapRecord) == 32, "snapshot record header");
+static const size_t SNAP_WINDOW = 64u << 20;
+
+extern "C" int cmb200_save(cmb200_engine *e, const char *path, uint64_t *records_out) {
+	std::lock_guard<std::mutex> g(e->mu);
+	unsigned long long c[8];
+	if (read_counters(e, c)) return -1;
+	const unsigned long long cap_out = c[0] + 16;
+	DevBuf d_list, d_count;
+	if (d_list.alloc(cap_out * sizeof(ExportEntry)) || d_count.alloc(8)) return -1;
+	CMB_CHECK(cudaMemsetAsync(d_count.p, 0, 8, e->st));
+	if (launch_export_list(e->table, e->bsize, d_list.as<ExportEntry>(), d_count.as<unsigned long long>(), cap_out, e->st)) return -1;
+	unsigned long long count = 0;
+	CMB_CHECK(cudaMemcpyAsync(&count, d_count.p, 8, cudaMemcpyDeviceToHost, e->st));
+	CMB_CHECK(cudaStreamSynchronize(e->st));
+	if (count > cap_out) count = cap_out;
+	std::vector<ExportEntry> list(count);
+	if (count) CMB_CHECK(cudaMemcpy(list.data(), d_list.p, count * sizeof(ExportEntry), cudaMemcpyDeviceToHost));
+	std::sort(list.begin(), list.end(), [](const ExportEntry &a, const ExportEntry &b) { return a.rec_off < b.rec_off; });
+
+	std::string tmp = std::string(path) + ".tmp";
+	FILE *f = fopen(tmp.c_str(), "wb");
+	if (!f) { set_error_msg("cmb200_save: cannot create the snapshot file"); return -1; }
+	SnapHeader h{};
+	memcpy(h.magic, "CMB200S1", 8);
+	h.version = 1; h.pshift = (uint32_t)e->pshift; h.records = count; h.flags = e->table.fp ? 1u : 0u;
+	for (const ExportEntry &x : list) h.bytes += x.len;
+	bool ok = fwrite(&h, sizeof(h), 1, f) == 1;
+	uint8_t *win = nullptr;
+	if (cudaMallocHost(&win, SNAP_WINDOW) != cudaSuccess) { fclose(f); remove(tmp.c_str()); set_error_msg("cmb200_save: no page-locked window"); return -1; }
+	static const uint8_t zeros[16] = {0};
+	size_t k = 0;
+	while (ok && k < list.size()) {
+		// one window of the arena starting at record k; the records wholly inside it are written out
+		const unsigned long long w0 = list[k].rec_off;
+		unsigned long long w1 = w0 + SNAP_WINDOW;
+		if (w1 > e->arena.size + 256) w1 = e->arena.size + 256;
+		if (cudaMemcpyAsync(win, e->arena.base + w0, (size_t)(w1 - w0), cudaMemcpyDeviceToHost, e->st) != cudaSuccess ||
+		    cudaStreamSynchronize(e->st) != cudaSuccess) { ok = false; break; }
+		for (; k < list.size() && list[k].rec_off + list[k].len <= w1; k++) {
+			const ExportEntry &x = list[k];
+			SnapRecord r{x.ts, x.fp_hi, x.fp_lo, x.len, 0};
+			const size_t padn = (16 - (x.len & 15)) & 15;
+			ok = ok && fwrite(&r, sizeof(r), 1, f) == 1 && fwrite(win + (x.rec_off - w0), x.len, 1, f) == 1 &&
+			    (padn == 0 || fwrite(zeros, padn, 1, f) == 1);
+		}
+	}
+	cudaFreeHost(win);
+	ok = ok && fflush(f) == 0;
+	ok = (fclose(f) == 0) && ok;
+	if (!ok || rename(tmp.c_str(), path) != 0) { remove(tmp.c_str()); set_error_msg("cmb200_save: write failed"); return -1; }
+	if (records_out) *records_out = count;
+	return 0;
+}
+
+extern "C" int cmb200_load(cmb200_engine *e, const char *path, uint64_t *records_out) {
+	std::lock_guard<std::mutex> g(e->mu);
+	CMB_CHECK(cudaSetDevice(e->device));
+	if (records_out) *records_out = 0;
+	FILE *f = fopen(path, "rb");
+	if (!f) { set_error_msg("cmb200_load: no snapshot file"); return -1; }
+	SnapHeader h{};
+	if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "CMB200S1", 8) != 0 || h.version != 1) {
+		fclose(f); set_error_msg("cmb200_load: not a snapshot of this library"); return -1;
+	}
+	if ((int)h.pshift != e->pshift) { fclose(f); set_error_msg("cmb200_load: snapshot has another page size"); return -1; }
+	// batches: <= max_batch records and <= one page-ring buffer of bytes
+	const size_t blob_cap = (size_t)e->host_batch * e->bsize;
+	const size_t B = e->max_batch < cmb200_engine::META_CAP ? e->max_batch : cmb200_engine::META_CAP;
+	uint8_t *blob = nullptr;
+	if (cudaMallocHost(&blob, blob_cap) != cudaSuccess) { fclose(f); set_error_msg("cmb200_load: no page-locked buffer"); return -1; }
+	std::vector<unsigned long long> off(B), ts(B), fps(2 * B);
+	std::vector<cmb200_addr> addr(B);
+	DevBuf d_off, d_fp;
+	int rc = 0;
+	if (d_off.alloc(B * 8) || d_fp.alloc(B * 16)) rc = -1;
+	uint64_t done = 0, loaded = 0;
+	SnapRecord pending{}; bool have_pending = false;
+	while (rc == 0 && done < h.records) {
+		size_t m = 0, used = 0;
+		while (m < B && done + m < h.records) {
+			SnapRecord r;
+			if (have_pending) { r = pending; have_pending = false; }
+			else if (fread(&r, sizeof(r), 1, f) != 1) { rc = -1; break; }
+			const size_t padded = ((size_t)r.len + 15) & ~(size_t)15;
+			if (r.len < 24 || r.len > 24u + e->bsize + 1024u) { rc = -1; break; }
+			if (used + padded > blob_cap) { pending = r; have_pending = true; break; }
+			if (fread(blob + used, padded, 1, f) != 1) { rc = -1; break; }
+			memcpy(&addr[m], blob + used, 16);      // data_prefix {u, l}
+			off[m] = used; ts[m] = r.ts; fps[2 * m] = r.fp_hi; fps[2 * m + 1] = r.fp_lo;
+			used += padded; m++;
+		}
+		if (rc) { set_error_msg("cmb200_load: truncated or corrupt snapshot"); break; }
+		if (m == 0) { rc = -1; set_error_msg("cmb200_load: record larger than the staging buffer"); break; }
+		const bool fail =
+		    cudaMemcpyAsync(e->d_pages[0], blob, used, cudaMemcpyHostToDevice, e->st) != cudaSuccess ||
+		    cudaMemcpyAsync(e->d_addr, addr.data(), m * 16, cudaMemcpyHostToDevice, e->st) != cudaSuccess ||
+		    cudaMemcpyAsync(e->d_ts, ts.data(), m * 8, cudaMemcpyHostToDevice, e->st) != cudaSuccess ||
+		    cudaMemcpyAsync(d_off.p, off.data(), m * 8, cudaMemcpyHostToDevice, e->st) != cudaSuccess ||
+		    cudaMemcpyAsync(d_fp.p, fps.data(), m * 16, cudaMemcpyHostToDevice, e->st) != cudaSuccess;
+		if (fail || launch_upsert(e->table, e->d_addr, nullptr, (uint32_t)m, e->seq, e->seq_stride, e->d_slot, e->st)) { rc = -1; break; }
+		EncodeJob job{};
+		job.n = (uint32_t)m; job.nbytes = e->bsize;
+		job.slot_idx = e->d_slot; job.addr = e->d_addr; job.ts = e->d_ts;
+		job.seq0 = e->seq; job.seq_stride = e->seq_stride;
+		job.table = e->table; job.arena = e->arena;
+		if (launch_restore(job, e->d_pages[0], d_off.as<unsigned long long>(), (h.flags & 1u) ? d_fp.as<uint64_t>() : nullptr,
+			e->bsize, e->st)) { rc = -1; break; }
+		if (cudaStreamSynchronize(e->st) != cudaSuccess) { rc = -1; break; }
+		e->seq += (unsigned long long)m * e->seq_stride;
+		e->stats.kernel_launches += 2;
+		done += m; loaded += m;
+	}
+	cudaFreeHost(blob);
+	fclose(f);
+	if (records_out) *records_out = loaded;
+	return rc;
+}
+
+// ---- kernel-level entry points -------------------------------------------------------------
 
 extern "C" int cmb200_compose_keys(int device, size_t n, const uint64_t *offset, const uint64_t *nhid,
     const uint32_t *genid, int pshift, cmb200_addr *addr_out, uint8_t *valid_out, uint64_t *key_out) {

@@ -807,6 +807,51 @@ int launch_read_fp(TableView t, const unsigned long long *addr, uint32_t n, uint
 	CMB_CHECK(cudaGetLastError());
 	return 0;
 }
+// ---- snapshot -----------------------------------------------------------------------------
+__global__ void k_export_list(TableView t, uint32_t bsize, ExportEntry *out, unsigned long long *count,
+    unsigned long long max_out) {
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= t.cap + 2) return;
+	const Slot &s = t.slots[i];
+	if (s.vlen == 0 || s.owner != 0) return;        // empty / deleted / the record lives on another GPU
+	if (i < t.cap && (s.key == KEY_EMPTY || s.key == KEY_TOMB)) return;
+	const unsigned long long j = atomicAdd(count, 1ull);
+	if (j >= max_out) return;
+	ExportEntry e;
+	e.rec_off = s.rec_off; e.ts = s.ts;
+	e.fp_hi = t.fp ? t.fp[2 * i] : 0ull; e.fp_lo = t.fp ? t.fp[2 * i + 1] : 0ull;
+	e.len = 24u + (s.vlen > 1u ? s.vlen - 1u : bsize);
+	e.slot = (uint32_t)i;
+	out[j] = e;
+}
+int launch_export_list(TableView t, uint32_t bsize, ExportEntry *out, unsigned long long *count,
+    unsigned long long max_out, cudaStream_t st) {
+	const uint64_t n = t.cap + 2;
+	k_export_list<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(t, bsize, out, count, max_out);
+	CMB_CHECK(cudaGetLastError());
+	return 0;
+}
+
+__global__ void __launch_bounds__(256) k_restore(EncodeJob job, const uint8_t *blob, const unsigned long long *off,
+    const uint64_t *fps, uint32_t bsize) {
+	const int lane = threadIdx.x & 31;
+	const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	if (i >= job.n) return;
+	const uint32_t idx = job.slot_idx[i];
+	if (idx == 0xffffffffu || job.table.slots[idx].seq != job.seq0 + job.seq_stride * i) return;
+	const uint8_t *rec = blob + off[i];
+	const int32_t clen = *reinterpret_cast<const int32_t *>(rec + 16);   // data_prefix.compressed_length (filemap.c:9-12); off[] is 16-aligned
+	const uint32_t plen = clen > 0 ? (uint32_t)clen : bsize;
+	commit_record(job, i, idx, rec + 24, plen, clen, true, fps ? fps[2 * i] : 0ull, fps ? fps[2 * i + 1] : 0ull, lane);
+}
+int launch_restore(const EncodeJob &job, const uint8_t *blob, const unsigned long long *off,
+    const uint64_t *fps, uint32_t bsize, cudaStream_t st) {
+	if (job.n == 0) return 0;
+	k_restore<<<(job.n * 32 + 255) / 256, 256, 0, st>>>(job, blob, off, fps, bsize);
+	CMB_CHECK(cudaGetLastError());
+	return 0;
+}
+
 int launch_sample(TableView t, const unsigned long long *r, uint32_t n, unsigned long long *addr_out,
     unsigned long long *ts_out, int32_t *ok, cudaStream_t st) {
 	if (n == 0) return 0;

@@ -127,6 +127,23 @@ int launch_read_fp(TableView t, const unsigned long long *addr, uint32_t n, uint
 int launch_streamgen(const uint64_t *cids, uint32_t n, uint64_t seed, uint32_t bsize, uint8_t *out,
     cudaStream_t st);
 
+// ---- snapshot of the store (persistence of the cache directory) ----
+// One entry per live local record, written by launch_export_list in arbitrary order.
+struct ExportEntry {
+	unsigned long long rec_off;  // arena offset of {data_prefix, payload}
+	unsigned long long ts;
+	unsigned long long fp_hi, fp_lo;
+	uint32_t len;                // 24 + payload bytes
+	uint32_t slot;
+};
+static_assert(sizeof(ExportEntry) == 40, "export entry layout");
+int launch_export_list(TableView t, uint32_t bsize, ExportEntry *out, unsigned long long *count,
+    unsigned long long max_out, cudaStream_t st);
+// Restores n records {24-byte prefix, payload} lying at blob + off[i]; slot_idx from launch_upsert
+// on the records' addresses (job.addr / job.ts / job.table / job.arena / job.seq0 as for a put).
+int launch_restore(const EncodeJob &job, const uint8_t *blob, const unsigned long long *off,
+    const uint64_t *fps, uint32_t bsize, cudaStream_t st);
+
 int sm_count();
 
 }  // namespace cmb

@@ -76,6 +76,16 @@ int cachemap_read_range(struct cachemap *cm, uint64_t nhid_small, uint32_t genid
 void cachemap_write_range(struct cachemap *cm, uint64_t nhid_small, uint32_t genid, uint64_t off,
     size_t size, const void *data);
 
+/*
+ * Persistence.  The reference's cache survives a restart because its store is a set of LMDB files
+ * in destdir (cachemap/filemap.c:57,71-72).  Here the store is in HBM: it is written to
+ * destdir/cachemap_b200.snap by cachemap_free, by cachemap_checkpoint, and every
+ * CMB200_CHECKPOINT_SEC seconds if that variable is set (edgefs never calls cachemap_free), and
+ * read back on the first put/get after cachemap_create on the same directory
+ * (CMB200_PERSIST=0 turns all of it off).  Returns 0 when a snapshot was written.
+ */
+int cachemap_checkpoint(struct cachemap *cm);
+
 /* requests / hits counters (cachemap.c:176,181) and the engine under the map. */
 void cachemap_get_counters(struct cachemap *cm, uint64_t *requests, uint64_t *hits);
 struct cmb200_engine *cachemap_engine(struct cachemap *cm);

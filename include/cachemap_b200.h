@@ -124,6 +124,17 @@ typedef struct cmb200_stats {
 } cmb200_stats;
 int cmb200_get_stats(cmb200_engine *e, cmb200_stats *out);
 
+/* ---- snapshot: what makes the cache directory persistent --------------------
+ * The reference's store is its LMDB files under <cachedir> (cachemap/filemap.c:57,71-72) and so
+ * survives a restart.  cmb200_save writes every live local record — byte for byte the LMDB value
+ * of the reference, 24-byte data_prefix + payload (filemap.c:140-147), with its timestamp
+ * attribute and fingerprint — to one file (written to path.tmp, then renamed); cmb200_load puts
+ * the records of such a file into the store as if they had been put in file order (existing keys
+ * are overwritten).  The format (engine.cu) is independent of capacity and arena size; the page
+ * size must match.  Both return 0 on success, -1 with cmb200_last_error() otherwise. */
+int cmb200_save(cmb200_engine *e, const char *path, uint64_t *records_out);
+int cmb200_load(cmb200_engine *e, const char *path, uint64_t *records_out);
+
 /* ---- multi-GPU: chunks sharded round-robin over ranks, one replicated key index per GPU ----
  * Each rank puts its own shard with the chunks' GLOBAL stream positions as sequence numbers
  * (next_seq = position of the rank's next chunk, stride = world size), then the ranks all-gather

@@ -457,3 +457,74 @@ def test_async_put_batches_overlap_and_stay_ordered(E, gpu, oracle):
     for p in [hp] + [x[0] for x in lens_pin]:
         E.lib().cmb200_host_free(p)
     eng.close()
+
+
+def test_cache_directory_survives_a_restart(E, gpu, oracle, tmp_path):
+    """The reference's store is its LMDB files, so a cache directory keeps its pages across
+    restarts (filemap.c:57,71-72).  Here cachemap_free / cachemap_checkpoint write
+    <dir>/cachemap_b200.snap and the next cachemap_create on that directory reads it back:
+    same hits, same pages, same record bytes, same entry count; counters start from zero."""
+    d = tmp_path / "cache"
+    d.mkdir()
+    n = 700
+    cm = E.Cachemap(str(d), 4096, 12, 16)
+    model = oracle.StoreModel(16, 12)
+    pages = [datagen.make_page("RTZMPAXS"[i % 8], 65536, 900 + i) for i in range(n)]
+    for i in range(n):
+        off, nh = (i % 500) << 16, 77 + (i % 3)          # some addresses are rewritten
+        cm.put(off, nh, 0, pages[i])
+        model.put(off, nh, 0, pages[i])
+    assert cm.checkpoint() == 0 and (d / "cachemap_b200.snap").exists()
+    cm.put(499 << 16, 77, 5, pages[0])                   # after the checkpoint: saved again by free
+    model.put(499 << 16, 77, 5, pages[0])
+    cm.free()
+
+    cm2 = E.Cachemap(str(d), 4096, 12, 16)
+    assert cm2.counters() == (0, 0)
+    for i in range(0, 500, 7):
+        for nh in (77, 78, 79):
+            got, want = cm2.get(i << 16, nh, 0), model.get(i << 16, nh, 0)
+            assert (got is None) == (want is None) and (got is None or got == bytes(want)), (i, nh)
+    assert cm2.get(499 << 16, 77, 5) == bytes(pages[0])
+    assert E.lib().cmb200_entries(cm2.engine_handle()) == model.entries()
+    cm2.free()
+
+    # a directory written with another page size is ignored (message on stderr), not misread
+    cm3 = E.Cachemap(str(d), 4096, 12, 12)
+    assert cm3.get(0, 77, 0) is None
+    cm3.put(0, 77, 0, pages[1][:4096])
+    assert cm3.get(0, 77, 0) == bytes(pages[1][:4096])
+    cm3.free()
+
+
+def test_engine_snapshot_roundtrip_any_geometry(E, gpu, oracle, tmp_path):
+    """cmb200_save / cmb200_load at the engine level: record bytes, timestamps and fingerprints come
+    back identical in an engine with a different capacity and arena; raw records (accel 0) too."""
+    n = 1200
+    pages = np.stack([E.gen_chunk_host(11, c, 65536) for c in range(n)])
+    u = np.full(n, 3, dtype=np.uint64)
+    l = np.arange(n, dtype=np.uint64)
+    ts = np.arange(n, dtype=np.uint64) + np.uint64(1000)
+    for accel in (12, 0):
+        a = E.Engine(pshift=16, accel=accel, capacity=4096, arena_bytes=256 << 20, max_batch=512, flags=E.FINGERPRINT)
+        a.put(u, l, pages, ts=ts)
+        a.unset(u[:100], l[:100])                                     # deleted records are not saved
+        path = str(tmp_path / f"snap{accel}")
+        assert a.save(path) == n - 100
+        b = E.Engine(pshift=16, accel=accel, capacity=65536, arena_bytes=1 << 30, max_batch=256, flags=E.FINGERPRINT)
+        assert b.load(path) == n - 100 and b.entries() == n - 100
+        ra, rb = a.read_records(u, l), b.read_records(u, l)
+        assert ra == rb and ra[0] is None and ra[100] is not None
+        fa, oka = a.read_fingerprints(u, l)
+        fb, okb = b.read_fingerprints(u, l)
+        assert (oka == okb).all() and (fa[oka != 0] == fb[okb != 0]).all()
+        out, st = b.get(u, l)
+        assert (st[:100] == E.MISS).all() and (st[100:] == E.HIT).all() and (out[100:] == pages[100:]).all()
+        r = np.arange(40, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+        _, tsb, okb2 = b.sample(r)
+        assert okb2.all() and ((tsb >= 1100) & (tsb < 1000 + n)).all()  # the LMDB attribute travels too
+        a.close(); b.close()
+    c = E.Engine(pshift=12, accel=12, capacity=4096, arena_bytes=64 << 20, max_batch=256)
+    with pytest.raises(Exception):
+        c.load(str(tmp_path / "snap12"))                               # other page size
+    c.close()
