@@ -31,6 +31,7 @@ EXPORTED_SYMBOLS = [
     "cmb200_unset_batch", "cmb200_entries", "cmb200_sample", "cmb200_read_records",
     "cmb200_read_fingerprints", "cmb200_get_stats", "cmb200_compose_keys",
     "cmb200_set_stream_order", "cmb200_import_remote", "cmb200_locate_batch", "cmb200_save", "cmb200_load",
+    "cmb200_put_step", "cmb200_import_records_dev",
     "cmb200_lz4_encode_batch", "cmb200_lz4_decode_batch", "cmb200_fingerprint_batch", "cmb200_fingerprint_dev",
     "cmb200_gen_chunk_host", "cmb200_gen_chunks_dev", "cmb200_gen_stream_ids", "cmb200_gen_addr",
 ]
@@ -51,7 +52,8 @@ class Stats(C.Structure):
 
 
 def library_path() -> str:
-    return os.path.join(_HERE, "libcachemap.so.0.0")
+    # CMB200_LIB: a differently tuned build of the same library (tools/build_variant.py)
+    return os.environ.get("CMB200_LIB") or os.path.join(_HERE, "libcachemap.so.0.0")
 
 
 def lib() -> C.CDLL:
@@ -105,6 +107,8 @@ def lib() -> C.CDLL:
         "cmb200_put_batch_dev": (i32, [vp, sz, vp, vp, vp, vp, vp]),
         "cmb200_put_batch_async": (i32, [vp, sz, vp, vp, vp, vp, vp, vp]),
         "cmb200_wait": (i32, [vp, u64]),
+        "cmb200_put_step": (i32, [vp, sz, vp, vp, vp, i32, vp, u32, vp, vp, vp]),
+        "cmb200_import_records_dev": (i32, [vp, sz, vp, u32]),
         "cmb200_save": (i32, [vp, C.c_char_p, vp]),
         "cmb200_load": (i32, [vp, C.c_char_p, vp]),
         "cmb200_get_batch": (i32, [vp, sz, vp, vp, vp, vp]),
@@ -291,6 +295,20 @@ class Engine:
         _check(lib().cmb200_put_batch_async(self.h, len(addr), _ptr(addr), _ptr(valid), _ptr(pages), _ptr(ts),
                                             _ptr(lens), C.byref(t)), "cmb200_put_batch_async")
         return t.value
+
+    def put_step(self, u, l, pages, ts=None, valid=None, on_dev=False, rank=0, records_dev=None, lens=None) -> int:
+        """cmb200_put_step: asynchronous put of one step of a sharded stream; exchange records are
+        written to the device buffer `records_dev` (n x 32 bytes).  -> ticket."""
+        addr = _addr_array(u, l)
+        ts = None if ts is None else np.ascontiguousarray(ts, dtype=np.uint64)
+        valid = None if valid is None else np.ascontiguousarray(valid, dtype=np.uint8)
+        t = C.c_uint64(0)
+        _check(lib().cmb200_put_step(self.h, len(addr), _ptr(addr), _ptr(valid), _ptr(pages), int(on_dev), _ptr(ts),
+                                     rank, _ptr(records_dev), _ptr(lens), C.byref(t)), "cmb200_put_step")
+        return t.value
+
+    def import_records_dev(self, n_total: int, records_dev, my_rank: int):
+        _check(lib().cmb200_import_records_dev(self.h, n_total, _ptr(records_dev), my_rank), "cmb200_import_records_dev")
 
     def wait(self, ticket: int):
         _check(lib().cmb200_wait(self.h, ticket), "cmb200_wait")

@@ -310,10 +310,15 @@ static void harvest_pending(cmb200_engine *e, bool wait) {
 // ticket != nullptr (host pages only): returns as soon as the caller's arrays have crossed to the
 // device; the encode of the last sub-batch (and the copy of lens_out, which must then be
 // page-locked and stay valid) completes behind the ticket.
+struct StepRecords { uint32_t rank; unsigned long long *out; };   // device-resident exchange records of a step
+
 static int put_slice(cmb200_engine *e, size_t n, const cmb200_addr *addr, const uint8_t *valid,
-    const uint8_t *pages, bool pages_on_dev, const uint64_t *ts, int32_t *lens_out, uint64_t *ticket) {
+    const uint8_t *pages, bool pages_on_dev, const uint64_t *ts, int32_t *lens_out, uint64_t *ticket,
+    const StepRecords *recs = nullptr) {
 	const size_t B = pages_on_dev ? e->max_batch : e->host_batch;
 	const bool deferred = ticket != nullptr;
+	const bool copy_meta = !pages_on_dev || deferred;      // small arrays travel on the copy stream
+	const unsigned long long seq_first = e->seq;
 	// stage the small arrays in page-locked memory once; every copy below is then truly async
 	cmb200_addr *h_addr = (cmb200_addr *)e->h_meta;
 	uint64_t *h_ts = (uint64_t *)(e->h_meta + cmb200_engine::META_CAP * 16);
@@ -329,16 +334,16 @@ static int put_slice(cmb200_engine *e, size_t n, const cmb200_addr *addr, const 
 	// the arrays that the previous call is not using: on the compute stream they would wait for
 	// the previous call's last encode, and the page copies issued after them would wait with them
 	// in the copy engine's queue.
-	const int mb = pages_on_dev ? 0 : (int)(e->meta_pos++ & 1);
+	const int mb = copy_meta ? (int)(e->meta_pos++ & 1) : 0;
 	unsigned long long *d_addr = e->d_addr + (size_t)mb * e->meta_cap * 2;
 	unsigned long long *d_ts = e->d_ts + (size_t)mb * e->meta_cap;
 	uint8_t *d_valid = e->d_valid + (size_t)mb * e->meta_cap;
-	cudaStream_t ms = pages_on_dev ? e->st : e->copy;
-	if (!pages_on_dev) CMB_CHECK(cudaStreamWaitEvent(e->copy, e->meta_free[mb], 0));
+	cudaStream_t ms = copy_meta ? e->copy : e->st;
+	if (copy_meta) CMB_CHECK(cudaStreamWaitEvent(e->copy, e->meta_free[mb], 0));
 	CMB_CHECK(cudaMemcpyAsync(d_addr, h_addr, n * 16, cudaMemcpyHostToDevice, ms));
 	if (valid) CMB_CHECK(cudaMemcpyAsync(d_valid, h_valid, n, cudaMemcpyHostToDevice, ms));
 	if (ts) CMB_CHECK(cudaMemcpyAsync(d_ts, h_ts, n * 8, cudaMemcpyHostToDevice, ms));
-	if (!pages_on_dev) {
+	if (copy_meta) {
 		CMB_CHECK(cudaEventRecord(e->meta_done, e->copy));
 		CMB_CHECK(cudaStreamWaitEvent(e->st, e->meta_done, 0));
 	}
@@ -399,14 +404,18 @@ static int put_slice(cmb200_engine *e, size_t n, const cmb200_addr *addr, const 
 		e->stats.kernel_launches += 2;
 	}
 	e->stats.put_chunks += n;
-	if (!pages_on_dev) CMB_CHECK(cudaEventRecord(e->meta_free[mb], e->st));
+	if (recs && recs->out) {
+		if (launch_pack_records(d_addr, e->d_lens, (uint32_t)n, seq_first, e->seq_stride, recs->rank, recs->out, e->st)) return -1;
+		e->stats.kernel_launches++;
+	}
+	if (copy_meta) CMB_CHECK(cudaEventRecord(e->meta_free[mb], e->st));
 	if (deferred) {
 		if (lens_out) CMB_CHECK(cudaMemcpyAsync(lens_out, e->d_lens, n * 4, cudaMemcpyDeviceToHost, e->st));
 		CMB_CHECK(cudaEventRecord(e->ticket_ev[e->tickets % cmb200_engine::TICKETS], e->st));
 		*ticket = ++e->tickets;
 		// the caller may reuse addr / valid / ts / pages once they have crossed
 		CMB_CHECK(cudaEventSynchronize(e->meta_done));
-		if (nb) CMB_CHECK(cudaEventSynchronize(e->landed[last_buf]));
+		if (nb && !pages_on_dev) CMB_CHECK(cudaEventSynchronize(e->landed[last_buf]));
 		harvest_pending(e, false);
 		return 0;
 	}
@@ -456,6 +465,31 @@ extern "C" int cmb200_put_batch_async(cmb200_engine *e, size_t n, const cmb200_a
 	if (ticket) *ticket = t;
 	return rc;
 }
+extern "C" int cmb200_put_step(cmb200_engine *e, size_t n, const cmb200_addr *addr, const uint8_t *valid,
+    const void *pages, int pages_on_dev, const uint64_t *ts, uint32_t rank, void *records_dev_out,
+    int32_t *lens_out, uint64_t *ticket) {
+	if (n > cmb200_engine::META_CAP) { set_error_msg("cmb200_put_step: more than 262144 chunks in one step"); return -1; }
+	std::lock_guard<std::mutex> g(e->mu);
+	CMB_CHECK(cudaSetDevice(e->device));
+	uint64_t t = e->tickets;
+	StepRecords r{rank, (unsigned long long *)records_dev_out};
+	const int rc = n ? put_slice(e, n, addr, valid, (const uint8_t *)pages, pages_on_dev != 0, ts, lens_out, &t, &r) : 0;
+	if (ticket) *ticket = t;
+	return rc;
+}
+
+extern "C" int cmb200_import_records_dev(cmb200_engine *e, size_t n_total, const void *records_dev, uint32_t my_rank) {
+	std::lock_guard<std::mutex> g(e->mu);
+	CMB_CHECK(cudaSetDevice(e->device));
+	const unsigned long long *rec = (const unsigned long long *)records_dev;
+	for (size_t at = 0; at < n_total; at += e->max_batch) {
+		const uint32_t m = (uint32_t)((n_total - at < e->max_batch) ? n_total - at : e->max_batch);
+		if (launch_import_records(e->table, e->arena, rec + 4 * at, m, my_rank, e->d_slot, e->st)) return -1;
+		e->stats.kernel_launches += 2;
+	}
+	return 0;                                               // asynchronous: ordered on the engine's stream
+}
+
 extern "C" int cmb200_wait(cmb200_engine *e, uint64_t ticket) {
 	cudaEvent_t ev = nullptr;
 	{

@@ -618,6 +618,9 @@ static int launch_encode_warps(const EncodeJob &job, cudaStream_t st) {
 	size_t smem = (size_t)warps * LZ4_TABLE_BYTES;
 	auto kern = job.nbytes >= LZ4_NARROW_LIMIT ? k_encode<true> : k_encode<false>;
 	CMB_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	// what the tables leave of the 256 KiB per SM is L1 for the page reads; -1 = driver's choice
+	static int carve = env_int("CMB200_ENC_CARVEOUT", -1, -1, 100);
+	if (carve >= 0) CMB_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
 	uint32_t grid = (uint32_t)(sm_count() * ctas);
 	uint32_t need = (job.n + warps - 1) / warps;
 	if (grid > need) grid = need;
@@ -768,6 +771,67 @@ int launch_import(TableView t, ArenaView a, const unsigned long long *addr, cons
 	CMB_CHECK(cudaGetLastError());
 	return 0;
 }
+// ---- multi-GPU exchange records, device resident ------------------------------------------------
+// One 32-byte record per chunk of a put step: {u, l, global stream position, owner rank << 32 | stored
+// length}; length < 0 = the chunk stored nothing (edge_fuse_b200/sharding.py has the same layout).
+__global__ void k_pack_records(const unsigned long long *addr, const int32_t *lens, uint32_t n,
+    unsigned long long seq0, unsigned long long stride, uint32_t rank, unsigned long long *out) {
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	ulonglong2 a = *reinterpret_cast<const ulonglong2 *>(addr + 2 * (size_t)i);
+	ulonglong2 b;
+	b.x = seq0 + stride * i;
+	b.y = ((unsigned long long)rank << 32) | (uint32_t)lens[i];
+	reinterpret_cast<ulonglong2 *>(out)[2 * (size_t)i] = a;
+	reinterpret_cast<ulonglong2 *>(out)[2 * (size_t)i + 1] = b;
+}
+int launch_pack_records(const unsigned long long *addr, const int32_t *lens, uint32_t n, unsigned long long seq0,
+    unsigned long long stride, uint32_t rank, unsigned long long *out, cudaStream_t st) {
+	if (n == 0) return 0;
+	k_pack_records<<<GRID1D(n), 0, st>>>(addr, lens, n, seq0, stride, rank, out);
+	CMB_CHECK(cudaGetLastError());
+	return 0;
+}
+// Import straight from all-gathered records: rows of `my_rank` and rows that stored nothing are skipped.
+__global__ void k_import_claim_rec(TableView t, const unsigned long long *rec, uint32_t n, uint32_t my_rank,
+    uint32_t *slot_idx) {
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const unsigned long long tail = rec[4 * (size_t)i + 3];
+	uint32_t idx = 0xffffffffu;
+	if ((uint32_t)(tail >> 32) != my_rank && (int32_t)(uint32_t)tail >= 0) {
+		idx = table_find_or_claim(t, fnv_addr(rec[4 * (size_t)i], rec[4 * (size_t)i + 1]));
+		if (idx != 0xffffffffu) atomicMax(&t.slots[idx].seq, rec[4 * (size_t)i + 2]);
+	}
+	slot_idx[i] = idx;
+}
+__global__ void k_import_apply_rec(TableView t, ArenaView a, const unsigned long long *rec, uint32_t n,
+    const uint32_t *slot_idx) {
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	uint32_t idx = slot_idx[i];
+	if (idx == 0xffffffffu) return;
+	Slot &s = t.slots[idx];
+	if (s.seq != rec[4 * (size_t)i + 2]) return;  // an even newer put (local or imported) owns the key
+	if (s.vlen) {                                 // our local record is superseded
+		atomicAdd(t.entries, (unsigned long long)-1ll);
+		atomicAdd(a.garbage, (unsigned long long)s.alloc);
+		s.vlen = 0; s.alloc = 0;
+	}
+	if (s.owner == 0) atomicAdd(t.remote, 1ull);
+	s.owner = (rec[4 * (size_t)i + 3] >> 32) + 1;
+	s.addr_u = rec[4 * (size_t)i]; s.addr_l = rec[4 * (size_t)i + 1];
+}
+int launch_import_records(TableView t, ArenaView a, const unsigned long long *rec, uint32_t n, uint32_t my_rank,
+    uint32_t *slot_idx, cudaStream_t st) {
+	if (n == 0) return 0;
+	k_import_claim_rec<<<GRID1D(n), 0, st>>>(t, rec, n, my_rank, slot_idx);
+	CMB_CHECK(cudaGetLastError());
+	k_import_apply_rec<<<GRID1D(n), 0, st>>>(t, a, rec, n, slot_idx);
+	CMB_CHECK(cudaGetLastError());
+	return 0;
+}
+
 int launch_upsert(TableView t, const unsigned long long *addr, const uint8_t *valid, uint32_t n,
     unsigned long long seq0, unsigned long long seq_stride, uint32_t *slot_idx, cudaStream_t st) {
 	if (n == 0) return 0;

@@ -111,6 +111,13 @@ int launch_upsert(TableView t, const unsigned long long *addr, const uint8_t *va
 int launch_import(TableView t, ArenaView a, const unsigned long long *addr, const uint32_t *owner,
     const unsigned long long *seq, uint32_t n, uint32_t *slot_idx, cudaStream_t st);
 
+// The same exchange with the records staying on the device: pack one 32-byte record per chunk of a
+// put step, import all-gathered records (rows of my_rank / rows that stored nothing are skipped).
+int launch_pack_records(const unsigned long long *addr, const int32_t *lens, uint32_t n, unsigned long long seq0,
+    unsigned long long stride, uint32_t rank, unsigned long long *out, cudaStream_t st);
+int launch_import_records(TableView t, ArenaView a, const unsigned long long *rec, uint32_t n, uint32_t my_rank,
+    uint32_t *slot_idx, cudaStream_t st);
+
 int launch_lookup(TableView t, const unsigned long long *addr, const uint8_t *valid, uint32_t n,
     int32_t *status, uint64_t *rec_off, uint32_t *vlen, unsigned long long *ts_out, cudaStream_t st);
 // After launch_lookup: status ST_REMOTE entries have their owner rank in rec_off[i].

@@ -73,11 +73,26 @@ template <> struct Lz4Table<true> {
 // aligned loads (page buffers are padded past their end; the word before the page start is never
 // needed because backward extension is capped by the position itself).
 struct Lz4Around { uint32_t before, at, next; };
+#ifndef CMB_LZ4_HINT_PROBE
+#define CMB_LZ4_HINT_PROBE 0
+#endif
+#ifndef CMB_LZ4_HINT_CAND
+#define CMB_LZ4_HINT_CAND 0
+#endif
+// HINT: 0 = ld.global.nc, 1 = + L1::evict_last, 2 = + L1::no_allocate (tuning, profiles/r1_encode_notes.md)
+template <int HINT> __device__ __forceinline__ uint32_t lz4_ldw(const uint32_t *q) {
+	uint32_t v;
+	if (HINT == 1) asm volatile("ld.global.nc.L1::evict_last.b32 %0, [%1];" : "=r"(v) : "l"(q));
+	else if (HINT == 2) asm volatile("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(v) : "l"(q));
+	else v = __ldg(q);
+	return v;
+}
+template <int HINT = 0>
 __device__ __forceinline__ Lz4Around lz4_around(const uint8_t *src, uint32_t p) {
 	const uint32_t a = p & ~3u, sh = (p & 3u) * 8u;
 	const uint32_t *q = reinterpret_cast<const uint32_t *>(src + a);
-	const uint32_t w0 = a ? __ldg(q - 1) : 0u;
-	const uint32_t w1 = __ldg(q), w2 = __ldg(q + 1), w3 = __ldg(q + 2);
+	const uint32_t w0 = a ? lz4_ldw<HINT>(q - 1) : 0u;
+	const uint32_t w1 = lz4_ldw<HINT>(q), w2 = lz4_ldw<HINT>(q + 1), w3 = lz4_ldw<HINT>(q + 2);
 	Lz4Around r;
 	r.before = __funnelshift_r(w0, w1, sh);
 	r.at = __funnelshift_r(w1, w2, sh);
@@ -260,14 +275,14 @@ __device__ uint32_t lz4_encode_warp(const uint8_t *__restrict__ src, uint32_t n,
 			const uint32_t litbyte = ldg8(src + min(anchor + lane, n - 1u));
 
 			// ---- unified batch ----
-			const Lz4Around ai = lz4_around(src, pos);
+			const Lz4Around ai = lz4_around<CMB_LZ4_HINT_PROBE>(src, pos);
 			const uint32_t pseq = ai.at;
 			const uint32_t h = WIDE ? lz4_hash5((uint64_t)ai.at | ((uint64_t)ai.next << 32)) : lz4_hash4(ai.at);
 			const uint32_t cand = tab.get(h);
 			__syncwarp();
 			if (en) tab.put(h, pos);                                // speculative commit
 			__syncwarp();
-			const Lz4Around ac = lz4_around(src, cand);             // latency overlaps the read-back
+			const Lz4Around ac = lz4_around<CMB_LZ4_HINT_CAND>(src, cand);   // latency overlaps the read-back
 			// (Lanes that share a slot store to it in the same instruction: CUDA guarantees that one
 			// of those stores lands; racecheck reports the write-write conflict, it is the mechanism.)
 			const uint32_t seen = tab.get(h);

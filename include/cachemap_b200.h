@@ -124,6 +124,19 @@ typedef struct cmb200_stats {
 } cmb200_stats;
 int cmb200_get_stats(cmb200_engine *e, cmb200_stats *out);
 
+/* One put step of a sharded stream with everything that follows it kept on the device and
+ * asynchronous.  Like cmb200_put_batch_async (pages on the host, pages_on_dev = 0) or its
+ * device-resident form (pages_on_dev = 1: the pages must stay untouched until the ticket is done),
+ * and additionally writes one 32-byte exchange record per chunk — {u, l, global stream position,
+ * rank << 32 | stored length (negative: nothing stored)} — to records_dev_out (device memory,
+ * n x 32 bytes) on the engine's stream.  The caller all-gathers those records (NCCL, on that
+ * stream) and hands the result to cmb200_import_records_dev, which imports the rows of the other
+ * ranks into the index replica, again without a host round trip.  n <= 262144. */
+int cmb200_put_step(cmb200_engine *e, size_t n, const cmb200_addr *addr, const uint8_t *valid,
+    const void *pages, int pages_on_dev, const uint64_t *ts, uint32_t rank, void *records_dev_out,
+    int32_t *lens_out, uint64_t *ticket);
+int cmb200_import_records_dev(cmb200_engine *e, size_t n_total, const void *records_dev, uint32_t my_rank);
+
 /* ---- snapshot: what makes the cache directory persistent --------------------
  * The reference's store is its LMDB files under <cachedir> (cachemap/filemap.c:57,71-72) and so
  * survives a restart.  cmb200_save writes every live local record — byte for byte the LMDB value

@@ -528,3 +528,55 @@ def test_engine_snapshot_roundtrip_any_geometry(E, gpu, oracle, tmp_path):
     with pytest.raises(Exception):
         c.load(str(tmp_path / "snap12"))                               # other page size
     c.close()
+
+
+def test_put_step_records_and_device_import(E, gpu, oracle):
+    """cmb200_put_step packs the exchange records of a step on the device exactly as sharding.py
+    packs them on the host, and cmb200_import_records_dev applies all-gathered records like
+    cmb200_import_remote: own rows and rows that stored nothing are skipped, the newest stream
+    position per key wins."""
+    from edge_fuse_b200 import sharding
+    n, world, rank = 512, 4, 1
+    eng = E.Engine(pshift=16, accel=12, capacity=8192, arena_bytes=128 << 20, max_batch=256, flags=E.FINGERPRINT)
+    pages = np.stack([E.gen_chunk_host(3, c, 65536) for c in range(n)])
+    d_pages = eng.dev_alloc(n * 65536)
+    eng.h2d(d_pages, pages)
+    d_rec = eng.dev_alloc(n * 32)
+    u = np.full(n, 21, dtype=np.uint64)
+    l = np.arange(n, dtype=np.uint64)
+    l[100] = l[40]                                                  # same key twice in the step: 40 is superseded
+    valid = np.ones(n, dtype=np.uint8); valid[7] = 0                # rejected address
+    base = 1000
+    eng.set_stream_order(base + rank, world)
+    for on_dev, src in ((True, d_pages), (False, pages)):
+        tk = eng.put_step(u, l, src, valid=valid, on_dev=on_dev, rank=rank, records_dev=d_rec)
+        eng.wait(tk); eng.sync()
+        got = np.zeros((n, 4), dtype=np.int64)
+        eng.d2h(got, d_rec)
+        pos = sharding.shard_positions(rank, world, n, base)
+        lens = np.array([len(oracle.lz4_encode(pages[i], 12)) for i in range(n)], dtype=np.int64)
+        lens[7] = -1; lens[40] = -1
+        assert (got == sharding.pack_records(u, l, pos, rank, lens)).all(), on_dev
+        base += world * n
+        eng.set_stream_order(base + rank, world)
+    assert eng.entries() == n - 2
+    # "all-gathered" rows: ours (ignored), another rank rewriting key 5 later (wins), another rank with
+    # an older position for key 6 (loses), a row that stored nothing (ignored), a new remote key
+    rows = np.array([
+        [21, 5, base + 10, (rank << 32) | 100],
+        [21, 5, base + 50, (2 << 32) | 200],
+        [21, 6, 3, (3 << 32) | 300],
+        [21, 9, base + 60, (2 << 32) | 0xFFFFFFFF],
+        [99, 1, base + 70, (0 << 32) | 400],
+    ], dtype=np.int64)
+    d_rows = eng.dev_alloc(rows.nbytes)
+    eng.h2d(d_rows, rows)
+    eng.import_records_dev(len(rows), d_rows, rank)
+    eng.sync()
+    status, owner = eng.locate(np.array([21, 21, 21, 99], dtype=np.uint64), np.array([5, 6, 9, 1], dtype=np.uint64))
+    assert list(status) == [E.REMOTE, E.HIT, E.HIT, E.REMOTE] and owner[0] == 2 and owner[3] == 0
+    st = eng.stats()
+    assert st["entries"] == n - 3 and st["remote_entries"] == 2
+    for p in (d_pages, d_rec, d_rows):
+        eng.dev_free(p)
+    eng.close()
