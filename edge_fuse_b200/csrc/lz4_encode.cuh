@@ -91,7 +91,9 @@ template <int HINT = 0>
 __device__ __forceinline__ Lz4Around lz4_around(const uint8_t *src, uint32_t p) {
 	const uint32_t a = p & ~3u, sh = (p & 3u) * 8u;
 	const uint32_t *q = reinterpret_cast<const uint32_t *>(src + a);
-	const uint32_t w0 = a ? lz4_ldw<HINT>(q - 1) : 0u;
+	// p < 4: the word before the page does not exist and is not needed (backward extension is capped
+	// by the position), so the first word is read twice instead of branching
+	const uint32_t w0 = lz4_ldw<HINT>(q - (a != 0u));
 	const uint32_t w1 = lz4_ldw<HINT>(q), w2 = lz4_ldw<HINT>(q + 1), w3 = lz4_ldw<HINT>(q + 2);
 	Lz4Around r;
 	r.before = __funnelshift_r(w0, w1, sh);
@@ -271,8 +273,9 @@ __device__ uint32_t lz4_encode_warp(const uint8_t *__restrict__ src, uint32_t n,
 				en = 2u + accel * (uint32_t)lane <= mflimit;
 			}
 			pos = en ? pos : 0u;                                   // keep disabled lanes' reads in range
-			// speculative literal byte: src[anchor + lane] (used when the run is <= 32 bytes)
+			// speculative literal bytes: src[anchor + lane], src[anchor + 32 + lane] (used when the run is <= 64 bytes)
 			const uint32_t litbyte = ldg8(src + min(anchor + lane, n - 1u));
+			const uint32_t litbyte2 = ldg8(src + min(anchor + 32u + lane, n - 1u));
 
 			// ---- unified batch ----
 			const Lz4Around ai = lz4_around<CMB_LZ4_HINT_PROBE>(src, pos);
@@ -347,18 +350,21 @@ __device__ uint32_t lz4_encode_warp(const uint8_t *__restrict__ src, uint32_t n,
 			const uint32_t end = ip + LZ4_MIN_MATCH + fwd;
 
 			// ---- emit: token, literal run (lz4.c:625-641), offset + match length (lz4.c:643-683) ----
-			if (lit <= 32u && mc < 15u + 255u) {
+			if (lit <= 64u && mc < 15u + 255u) {
 				uint8_t *o = dst + op;
-				const uint32_t hl = 1u + (lit >= 15u);
-				const uint32_t mext = mc >= 15u;
+				const uint32_t lext = lit >= 15u, mext = mc >= 15u;
+				const uint32_t hl = 1u + lext;
 				if ((uint32_t)lane < lit) o[hl + lane] = (uint8_t)litbyte;
-				// lanes 0-4 each own one of the bytes around the literals
+				if ((uint32_t)lane + 32u < lit) o[hl + 32u + lane] = (uint8_t)litbyte2;
+				// lanes 0-4 each own one of the bytes around the literals: token, literal length
+				// byte, offset low, offset high, match length byte (no branches: byte `lane` of a
+				// packed word, written if the lane's bit of `owners` is set)
 				const uint32_t tail = hl + lit;
-				const uint32_t at = lane == 0 ? 0u : lane == 1 ? 1u : tail + (uint32_t)lane - 2u;
-				const uint32_t val = lane == 0 ? ((min(lit, 15u) << 4) | min(mc, 15u)) : lane == 1 ? lit - 15u
-				    : lane == 2 ? off : lane == 3 ? off >> 8 : mc - 15u;
-				const bool own = lane == 0 || (lane == 1 && lit >= 15u) || lane == 2 || lane == 3 || (lane == 4 && mext);
-				if (own) o[at] = (uint8_t)val;
+				const uint32_t head4 = (min(lit, 15u) << 4) | min(mc, 15u) | (((lit - 15u) & 0xffu) << 8) | (off << 16);
+				const uint32_t val = lane < 4 ? head4 >> (8u * (uint32_t)lane) : mc - 15u;
+				const uint32_t at = lane < 2 ? (uint32_t)lane : tail + (uint32_t)lane - 2u;
+				const uint32_t owners = 0x0du | (lext << 1) | (mext << 4);
+				if ((owners >> lane) & 1u) o[at] = (uint8_t)val;
 				op += tail + 2u + mext;
 			} else {
 				op = lz4_emit_general(dst, op, src, anchor, lit, off, mc, lane);
