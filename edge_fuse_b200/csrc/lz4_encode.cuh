@@ -79,11 +79,16 @@ struct Lz4Around { uint32_t before, at, next; };
 #ifndef CMB_LZ4_HINT_CAND
 #define CMB_LZ4_HINT_CAND 0
 #endif
-// HINT: 0 = ld.global.nc, 1 = + L1::evict_last, 2 = + L1::no_allocate (tuning, profiles/r1_encode_notes.md)
+// HINT: 0 = ld.global.nc, 1 = + L1::evict_last, 2 = + L1::no_allocate, 3 = .cg, 4 = .cs, 5 = .lu,
+// 6 = .nc + L1::evict_first (tuning, profiles/r1_encode_notes.md)
 template <int HINT> __device__ __forceinline__ uint32_t lz4_ldw(const uint32_t *q) {
 	uint32_t v;
-	if (HINT == 1) asm volatile("ld.global.nc.L1::evict_last.b32 %0, [%1];" : "=r"(v) : "l"(q));
-	else if (HINT == 2) asm volatile("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(v) : "l"(q));
+	if (HINT == 1) asm("ld.global.nc.L1::evict_last.b32 %0, [%1];" : "=r"(v) : "l"(q));
+	else if (HINT == 2) asm("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(v) : "l"(q));
+	else if (HINT == 3) v = __ldcg(q);
+	else if (HINT == 4) v = __ldcs(q);
+	else if (HINT == 5) v = __ldlu(q);
+	else if (HINT == 6) asm("ld.global.nc.L1::evict_first.b32 %0, [%1];" : "=r"(v) : "l"(q));
 	else v = __ldg(q);
 	return v;
 }
