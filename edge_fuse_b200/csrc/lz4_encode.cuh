@@ -315,7 +315,9 @@ __device__ uint32_t lz4_encode_warp(const uint8_t *__restrict__ src, uint32_t n,
 			const uint32_t low_hit = hits & (0u - hits), low_for = foreigns & (0u - foreigns);
 			uint32_t ip, match, fwd, back;
 			bool retest_hit;
-			if (hits != 0u && (foreigns == 0u || low_hit < low_for)) {
+			// one compare: with no hit low_hit - 1 is 0xffffffff (never smaller), with no foreign lane
+			// low_for - 1 is 0xffffffff (any hit is smaller)
+			if (low_hit - 1u < low_for - 1u) {
 				const int w = __ffs(hits) - 1;
 				// put the old value back past the winner, unless the slot now holds the position
 				// of a lane at or before the winner (a committed write that must stay)
@@ -327,9 +329,11 @@ __device__ uint32_t lz4_encode_warp(const uint8_t *__restrict__ src, uint32_t n,
 				fwd = __shfl_sync(CMB_FULL, nf, w);
 				back = __shfl_sync(CMB_FULL, nb, w);
 				retest_hit = (uint32_t)w < shift;
-				if (fwd == 4u) fwd = 4u + lz4_count_long(src, ip + 8u, match + 8u, mlimit, lim4, lane);
-				if (back == 4u && ip >= anchor + 5u && match >= 5u)
-					back = 4u + lz4_catchup_long(src, ip - 4u, match - 4u, anchor, lane);
+				if (fwd == 4u || back == 4u) {                      // longer than the neighbourhoods show: rare
+					if (fwd == 4u) fwd = 4u + lz4_count_long(src, ip + 8u, match + 8u, mlimit, lim4, lane);
+					if (back == 4u && ip >= anchor + 5u && match >= 5u)
+						back = 4u + lz4_catchup_long(src, ip - 4u, match - 4u, anchor, lane);
+				}
 			} else {
 				uint64_t res = 0;
 				const uint32_t enmask = __ballot_sync(CMB_FULL, en);
