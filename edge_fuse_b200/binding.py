@@ -31,7 +31,7 @@ EXPORTED_SYMBOLS = [
     "cmb200_unset_batch", "cmb200_entries", "cmb200_sample", "cmb200_read_records",
     "cmb200_read_fingerprints", "cmb200_get_stats", "cmb200_compose_keys",
     "cmb200_set_stream_order", "cmb200_import_remote", "cmb200_locate_batch", "cmb200_save", "cmb200_load",
-    "cmb200_put_step", "cmb200_import_records_dev",
+    "cmb200_put_step", "cmb200_import_records_dev", "cmb200_compact",
     "cmb200_lz4_encode_batch", "cmb200_lz4_decode_batch", "cmb200_fingerprint_batch", "cmb200_fingerprint_dev",
     "cmb200_gen_chunk_host", "cmb200_gen_chunks_dev", "cmb200_gen_stream_ids", "cmb200_gen_addr",
 ]
@@ -109,6 +109,7 @@ def lib() -> C.CDLL:
         "cmb200_wait": (i32, [vp, u64]),
         "cmb200_put_step": (i32, [vp, sz, vp, vp, vp, i32, vp, u32, vp, vp, vp]),
         "cmb200_import_records_dev": (i32, [vp, sz, vp, u32]),
+        "cmb200_compact": (i32, [vp, vp]),
         "cmb200_save": (i32, [vp, C.c_char_p, vp]),
         "cmb200_load": (i32, [vp, C.c_char_p, vp]),
         "cmb200_get_batch": (i32, [vp, sz, vp, vp, vp, vp]),
@@ -358,6 +359,12 @@ class Engine:
         _check(lib().cmb200_read_fingerprints(self.h, n, _ptr(addr), _ptr(fps), _ptr(ok)),
                "cmb200_read_fingerprints")
         return fps, ok
+
+    def compact(self) -> int:
+        """cmb200_compact -> bytes of arena reclaimed."""
+        n = C.c_uint64(0)
+        _check(lib().cmb200_compact(self.h, C.byref(n)), "cmb200_compact")
+        return n.value
 
     def save(self, path: str) -> int:
         n = C.c_uint64(0)

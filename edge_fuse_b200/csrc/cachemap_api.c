@@ -259,8 +259,25 @@ filemap_free(struct filemap *m)
 /* Makes room for `incoming` puts: while entries + incoming > capacity, retire the oldest of three
  * random live records (cachemap.c:17-45).  Statistically the reference's policy; bitwise parity
  * is undefined there (wall-clock timestamps, rand()). */
+/* The arena is a bump allocator; when `incoming` more worst-case records would not fit although a
+ * good part of it is garbage (deleted and outgrown records), compact it first.  A full arena
+ * drops puts, as a full LMDB map does (filemap.c:143-145,154-157). */
 static void
-filemap_make_room(struct filemap *m, uint64_t incoming)
+filemap_check_arena(struct filemap *m, uint64_t incoming)
+{
+	cmb200_stats st;
+	if (cmb200_get_stats(m->eng, &st) != 0)
+		return;
+	uint64_t need = incoming * ((uint64_t)m->bsize + 1056);
+	if (st.arena_used + need <= st.arena_bytes || st.arena_garbage < st.arena_bytes / 16)
+		return;
+	uint64_t got = 0;
+	if (cmb200_compact(m->eng, &got) != 0)
+		fprintf(stderr, "cachemap_b200: arena compaction failed: %s\n", cmb200_last_error());
+}
+
+static void
+filemap_evict(struct filemap *m, uint64_t incoming)
 {
 	if (!m->capacity)
 		return;
@@ -299,6 +316,8 @@ filemap_make_room(struct filemap *m, uint64_t incoming)
 				}
 				if (nv)
 					cmb200_unset_batch(m->eng, (size_t)nv, victim);
+			} else {
+				fprintf(stderr, "cachemap_b200: eviction could not sample the store: %s\n", cmb200_last_error());
 			}
 		}
 		free(draws); free(ts); free(ok); free(cand); free(victim);
@@ -307,6 +326,15 @@ filemap_make_room(struct filemap *m, uint64_t incoming)
 		if (incoming == 1)
 			return;         /* the reference evicts exactly one per put */
 	}
+}
+
+/* Before a batch of `incoming` puts: evict down to capacity, then make sure the arena has room
+ * (what eviction frees is garbage until the arena is compacted). */
+static void
+filemap_make_room(struct filemap *m, uint64_t incoming)
+{
+	filemap_evict(m, incoming);
+	filemap_check_arena(m, incoming);
 }
 
 /* The flusher: takes the longest run of finished slots from the tail of the ring and puts it

@@ -672,15 +672,16 @@ extern "C" int cmb200_sample(cmb200_engine *e, size_t n, const uint64_t *r, cmb2
     uint64_t *ts_out, int32_t *ok_out) {
 	std::lock_guard<std::mutex> g(e->mu);
 	CMB_CHECK(cudaSetDevice(e->device));
-	if (n > e->max_batch) { set_error_msg("cmb200_sample: n exceeds max_batch"); return -1; }
-	uint32_t m = (uint32_t)n;
-	CMB_CHECK(cudaMemcpyAsync(e->d_recoff, r, n * 8, cudaMemcpyHostToDevice, e->st));
-	if (launch_sample(e->table, (const unsigned long long *)e->d_recoff, m, e->d_addr, e->d_ts, e->d_status, e->st)) return -1;
-	CMB_CHECK(cudaMemcpyAsync(addr_out, e->d_addr, n * 16, cudaMemcpyDeviceToHost, e->st));
-	CMB_CHECK(cudaMemcpyAsync(ts_out, e->d_ts, n * 8, cudaMemcpyDeviceToHost, e->st));
-	CMB_CHECK(cudaMemcpyAsync(ok_out, e->d_status, n * 4, cudaMemcpyDeviceToHost, e->st));
-	CMB_CHECK(cudaStreamSynchronize(e->st));
-	e->stats.kernel_launches++;
+	for (size_t at = 0; at < n; at += e->max_batch) {
+		const uint32_t m = (uint32_t)((n - at < e->max_batch) ? n - at : e->max_batch);
+		CMB_CHECK(cudaMemcpyAsync(e->d_recoff, r + at, (size_t)m * 8, cudaMemcpyHostToDevice, e->st));
+		if (launch_sample(e->table, (const unsigned long long *)e->d_recoff, m, e->d_addr, e->d_ts, e->d_status, e->st)) return -1;
+		CMB_CHECK(cudaMemcpyAsync(addr_out + at, e->d_addr, (size_t)m * 16, cudaMemcpyDeviceToHost, e->st));
+		CMB_CHECK(cudaMemcpyAsync(ts_out + at, e->d_ts, (size_t)m * 8, cudaMemcpyDeviceToHost, e->st));
+		CMB_CHECK(cudaMemcpyAsync(ok_out + at, e->d_status, (size_t)m * 4, cudaMemcpyDeviceToHost, e->st));
+		CMB_CHECK(cudaStreamSynchronize(e->st));
+		e->stats.kernel_launches++;
+	}
 	return 0;
 }
 
@@ -873,6 +874,59 @@ extern "C" int cmb200_load(cmb200_engine *e, const char *path, uint64_t *records
 	fclose(f);
 	if (records_out) *records_out = loaded;
 	return rc;
+}
+
+// ---- arena compaction -------------------------------------------------------------------------
+// The arena is a bump allocator: a deleted record, or one that outgrew its place, leaves its bytes
+// behind as garbage.  Compaction slides the live records down to the start of the arena (sorted by
+// offset, so every record moves to a lower or equal address), window by window through one of the
+// page-ring buffers, repoints the slots and resets the bump pointer and the per-warp segments.
+// Stop-the-world on the engine's stream, at HBM speed; callers trigger it when the arena is about
+// to overflow although a good part of it is garbage (filemap_make_room, cmb200_compact).
+extern "C" int cmb200_compact(cmb200_engine *e, uint64_t *reclaimed_out) {
+	std::lock_guard<std::mutex> g(e->mu);
+	unsigned long long c[8];
+	if (read_counters(e, c)) return -1;
+	harvest_pending(e, true);
+	const unsigned long long head_before = c[2];
+	const unsigned long long cap_out = c[0] + 16;
+	DevBuf d_list, d_count, d_moves;
+	if (d_list.alloc(cap_out * sizeof(ExportEntry)) || d_count.alloc(8)) return -1;
+	CMB_CHECK(cudaMemsetAsync(d_count.p, 0, 8, e->st));
+	if (launch_export_list(e->table, e->bsize, d_list.as<ExportEntry>(), d_count.as<unsigned long long>(), cap_out, e->st)) return -1;
+	unsigned long long count = 0;
+	CMB_CHECK(cudaMemcpyAsync(&count, d_count.p, 8, cudaMemcpyDeviceToHost, e->st));
+	CMB_CHECK(cudaStreamSynchronize(e->st));
+	if (count > cap_out) { set_error_msg("cmb200_compact: the store changed under the compaction"); return -1; }
+	std::vector<ExportEntry> list(count);
+	if (count) CMB_CHECK(cudaMemcpy(list.data(), d_list.p, count * sizeof(ExportEntry), cudaMemcpyDeviceToHost));
+	std::sort(list.begin(), list.end(), [](const ExportEntry &a, const ExportEntry &b) { return a.rec_off < b.rec_off; });
+	std::vector<MoveEntry> moves(count);
+	unsigned long long at = 0;
+	for (size_t i = 0; i < count; i++) {
+		moves[i] = MoveEntry{list[i].rec_off, at, list[i].len, list[i].slot};
+		at += ((unsigned long long)list[i].len + 15ull) & ~15ull;
+	}
+	if (count && d_moves.alloc(count * sizeof(MoveEntry))) return -1;
+	if (count) CMB_CHECK(cudaMemcpyAsync(d_moves.p, moves.data(), count * sizeof(MoveEntry), cudaMemcpyHostToDevice, e->st));
+	// windows: as many records as fit the bounce buffer (one page-ring buffer)
+	const unsigned long long bounce_cap = (unsigned long long)e->host_batch * e->bsize;
+	size_t k = 0;
+	while (k < count) {
+		size_t j = k;
+		while (j < count && moves[j].new_off + (((unsigned long long)moves[j].len + 15ull) & ~15ull) - moves[k].new_off <= bounce_cap) j++;
+		if (j == k) { set_error_msg("cmb200_compact: record larger than the bounce buffer"); return -1; }
+		if (launch_compact_window(e->table, e->arena, d_moves.as<MoveEntry>() + k, (uint32_t)(j - k), e->d_pages[0], e->st)) return -1;
+		e->stats.kernel_launches += 2;
+		k = j;
+	}
+	// bump pointer back to the end of the live records, no garbage, no half-used segments
+	unsigned long long fresh[2] = {at, 0};
+	CMB_CHECK(cudaMemcpyAsync(e->d_counters + 2, fresh, 16, cudaMemcpyHostToDevice, e->st));
+	CMB_CHECK(cudaMemsetAsync(e->arena.seg, 0, ARENA_SEG_SLOTS * 2 * sizeof(unsigned long long), e->st));
+	CMB_CHECK(cudaStreamSynchronize(e->st));
+	if (reclaimed_out) *reclaimed_out = head_before > at ? head_before - at : 0;
+	return 0;
 }
 
 // ---- kernel-level entry points -------------------------------------------------------------

@@ -916,6 +916,39 @@ int launch_restore(const EncodeJob &job, const uint8_t *blob, const unsigned lon
 	return 0;
 }
 
+// ---- arena compaction ---------------------------------------------------------------------
+// moves[i].new_off - moves[0].new_off is also the record's place in the bounce buffer (records are
+// packed in the same order and with the same 16-byte rounding in both).
+__global__ void __launch_bounds__(256) k_compact_gather(ArenaView a, const MoveEntry *moves, uint32_t n, uint8_t *bounce) {
+	const int lane = threadIdx.x & 31;
+	const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	if (i >= n) return;
+	const MoveEntry m = moves[i];
+	warp_copy_rw(bounce + (m.new_off - moves[0].new_off), a.base + m.old_off, m.len, lane);
+}
+__global__ void __launch_bounds__(256) k_compact_scatter(TableView t, ArenaView a, const MoveEntry *moves, uint32_t n,
+    const uint8_t *bounce) {
+	const int lane = threadIdx.x & 31;
+	const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	if (i >= n) return;
+	const MoveEntry m = moves[i];
+	warp_copy_rw(a.base + m.new_off, bounce + (m.new_off - moves[0].new_off), m.len, lane);
+	if (lane == 0) {
+		Slot &s = t.slots[m.slot];
+		s.rec_off = m.new_off;
+		s.alloc = (m.len + 15u) & ~15u;
+	}
+}
+int launch_compact_window(TableView t, ArenaView a, const MoveEntry *moves, uint32_t n, uint8_t *bounce,
+    cudaStream_t st) {
+	if (n == 0) return 0;
+	k_compact_gather<<<(n * 32 + 255) / 256, 256, 0, st>>>(a, moves, n, bounce);
+	CMB_CHECK(cudaGetLastError());
+	k_compact_scatter<<<(n * 32 + 255) / 256, 256, 0, st>>>(t, a, moves, n, bounce);
+	CMB_CHECK(cudaGetLastError());
+	return 0;
+}
+
 int launch_sample(TableView t, const unsigned long long *r, uint32_t n, unsigned long long *addr_out,
     unsigned long long *ts_out, int32_t *ok, cudaStream_t st) {
 	if (n == 0) return 0;

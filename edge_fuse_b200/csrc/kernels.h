@@ -151,6 +151,15 @@ int launch_export_list(TableView t, uint32_t bsize, ExportEntry *out, unsigned l
 int launch_restore(const EncodeJob &job, const uint8_t *blob, const unsigned long long *off,
     const uint64_t *fps, uint32_t bsize, cudaStream_t st);
 
+// ---- arena compaction (space of deleted / outgrown records comes back) ----
+// Moves n records (sorted by old offset, new offset <= old offset) down in two steps per window so
+// that no record is overwritten before it has been read: gather into `bounce`, then scatter to the
+// new offsets and repoint the slots.
+struct MoveEntry { unsigned long long old_off, new_off; uint32_t len, slot; };
+static_assert(sizeof(MoveEntry) == 24, "move entry layout");
+int launch_compact_window(TableView t, ArenaView a, const MoveEntry *moves, uint32_t n, uint8_t *bounce,
+    cudaStream_t st);
+
 int sm_count();
 
 }  // namespace cmb

@@ -137,6 +137,12 @@ int cmb200_put_step(cmb200_engine *e, size_t n, const cmb200_addr *addr, const u
     int32_t *lens_out, uint64_t *ticket);
 int cmb200_import_records_dev(cmb200_engine *e, size_t n_total, const void *records_dev, uint32_t my_rank);
 
+/* Slides the live records to the start of the arena so that the space of deleted and outgrown
+ * records (stats.arena_garbage, and the unused remainders of per-warp segments) can be allocated
+ * again; *reclaimed_out = bytes by which stats.arena_used went down.  Blocks the engine while it
+ * runs (HBM speed).  The cachemap layer calls it by itself when the arena is about to overflow. */
+int cmb200_compact(cmb200_engine *e, uint64_t *reclaimed_out);
+
 /* ---- snapshot: what makes the cache directory persistent --------------------
  * The reference's store is its LMDB files under <cachedir> (cachemap/filemap.c:57,71-72) and so
  * survives a restart.  cmb200_save writes every live local record — byte for byte the LMDB value

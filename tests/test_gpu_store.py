@@ -580,3 +580,74 @@ def test_put_step_records_and_device_import(E, gpu, oracle):
     for p in (d_pages, d_rec, d_rows):
         eng.dev_free(p)
     eng.close()
+
+
+def test_arena_compaction_reclaims_deleted_and_outgrown_records(E, gpu, oracle):
+    """cmb200_compact slides the live records down: arena_used falls to the live bytes, garbage to
+    zero, and every record, timestamp and fingerprint is what it was (staged and in-place paths)."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, os
+sys.path.insert(0, os.getcwd())
+import numpy as np, edge_fuse_b200 as E
+n = 1500
+eng = E.Engine(pshift=16, accel=12, capacity=8192, arena_bytes=int(os.environ["ARENA"]), max_batch=512, flags=E.FINGERPRINT)
+u = np.full(n, 4, dtype=np.uint64); l = np.arange(n, dtype=np.uint64)
+small = np.stack([E.gen_chunk_host(1, 8 * c + 2, 65536) for c in range(n)])       # Z class: tiny records
+big = np.stack([E.gen_chunk_host(1, 8 * c + 0, 65536) for c in range(n)])         # R class: outgrow them
+eng.put(u, l, small, ts=np.arange(n, dtype=np.uint64))
+eng.put(u[::2], l[::2], np.ascontiguousarray(big[::2]), ts=np.arange(n, dtype=np.uint64)[::2] + 5000)   # every other key outgrows its record
+eng.unset(u[1::4], l[1::4])                                                        # and a quarter is deleted
+before = eng.stats()
+recs = eng.read_records(u, l); fps, ok = eng.read_fingerprints(u, l)
+got = eng.compact()
+after = eng.stats()
+assert after["entries"] == before["entries"] and after["arena_garbage"] == 0 and got > 0
+live = sum((len(r) + 15) & ~15 for r in recs if r is not None)
+assert after["arena_used"] == live and before["arena_used"] - after["arena_used"] == got, (after, live, got)
+assert eng.read_records(u, l) == recs
+fps2, ok2 = eng.read_fingerprints(u, l)
+assert (ok == ok2).all() and (fps[ok != 0] == fps2[ok2 != 0]).all()
+out, st = eng.get(u, l)
+want = small.copy(); want[::2] = big[::2]
+hit = st == E.HIT
+assert (hit == np.array([r is not None for r in recs])).all() and (out[hit] == want[hit]).all()
+# the store keeps working: new puts land after the compacted records
+eng.put(u[1::4], l[1::4], np.ascontiguousarray(big[1::4]))
+out, st = eng.get(u, l)
+assert (st == E.HIT).all() and (out[1::4] == big[1::4]).all() and eng.stats()["dropped_puts"] == 0
+assert eng.compact() >= 0                                                          # idempotent on a tidy arena
+print("compact ok", before["arena_used"], after["arena_used"])
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for arena, seg in ((256 << 20, "0"), (1 << 30, "320")):                    # staged path / in-place path
+        env = dict(os.environ, ARENA=str(arena), CMB200_SEG_KB=seg)
+        out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=900)
+        assert out.returncode == 0 and "compact ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_cache_outlives_many_times_its_arena(E, gpu, tmp_path, monkeypatch):
+    """A cache that runs for a long time writes many times its arena.  With eviction holding the
+    entry count at `capacity` and compaction reclaiming what eviction frees, no put is ever
+    dropped and the newest pages are always readable (the reference's LMDB reuses freed pages)."""
+    monkeypatch.setenv("CMB200_ARENA_MB", "96")
+    monkeypatch.setenv("CMB200_SEG_KB", "0")
+    cap = 1024
+    cm = E.Cachemap(str(tmp_path), cap, 12, 16)
+    pages = np.stack([E.gen_chunk_host(9, 8 * c, 65536) for c in range(256)])     # incompressible: 64 KiB records
+    total = 6000                                                                    # ~375 MiB through a 96 MiB arena
+    for base in range(0, total, 256):
+        k = min(256, total - base)
+        off = (np.arange(base, base + k, dtype=np.uint64)) << np.uint64(16)
+        cm.put_batch(off, np.full(k, 3, dtype=np.uint64), np.zeros(k, dtype=np.uint32), pages[:k])
+    import ctypes
+    from edge_fuse_b200.binding import Stats
+    eng_stats = Stats()
+    assert E.lib().cmb200_get_stats(cm.engine_handle(), ctypes.byref(eng_stats)) == 0
+    assert eng_stats.dropped_puts == 0 and eng_stats.entries <= cap
+    # the pages of the last batch (put after the last eviction) are all there
+    off = (np.arange(total - 100, total, dtype=np.uint64)) << np.uint64(16)
+    out, hit = cm.get_batch(off, np.full(100, 3, dtype=np.uint64), np.zeros(100, dtype=np.uint32))
+    assert hit.all() and (out == pages[(np.arange(total - 100, total) % 256)]).all()
+    cm.free()
