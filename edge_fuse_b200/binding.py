@@ -299,7 +299,9 @@ class Engine:
 
     def put_step(self, u, l, pages, ts=None, valid=None, on_dev=False, rank=0, records_dev=None, lens=None) -> int:
         """cmb200_put_step: asynchronous put of one step of a sharded stream; exchange records are
-        written to the device buffer `records_dev` (n x 32 bytes).  -> ticket."""
+        written to the device buffer `records_dev` (n x 32 bytes).  on_dev: False = host pages,
+        reusable on return; True = device pages; 2 = page-locked host pages the caller keeps
+        untouched until wait(ticket).  -> ticket."""
         addr = _addr_array(u, l)
         ts = None if ts is None else np.ascontiguousarray(ts, dtype=np.uint64)
         valid = None if valid is None else np.ascontiguousarray(valid, dtype=np.uint8)

@@ -310,7 +310,9 @@ static void harvest_pending(cmb200_engine *e, bool wait) {
 // ticket != nullptr (host pages only): returns as soon as the caller's arrays have crossed to the
 // device; the encode of the last sub-batch (and the copy of lens_out, which must then be
 // page-locked and stay valid) completes behind the ticket.
-struct StepRecords { uint32_t rank; unsigned long long *out; };   // device-resident exchange records of a step
+// device-resident exchange records of a step; keep_pages: the caller keeps the host pages untouched
+// until the ticket is done, so the call need not wait for its own copies
+struct StepRecords { uint32_t rank; unsigned long long *out; bool keep_pages; };
 
 static int put_slice(cmb200_engine *e, size_t n, const cmb200_addr *addr, const uint8_t *valid,
     const uint8_t *pages, bool pages_on_dev, const uint64_t *ts, int32_t *lens_out, uint64_t *ticket,
@@ -415,7 +417,7 @@ static int put_slice(cmb200_engine *e, size_t n, const cmb200_addr *addr, const 
 		*ticket = ++e->tickets;
 		// the caller may reuse addr / valid / ts / pages once they have crossed
 		CMB_CHECK(cudaEventSynchronize(e->meta_done));
-		if (nb && !pages_on_dev) CMB_CHECK(cudaEventSynchronize(e->landed[last_buf]));
+		if (nb && !pages_on_dev && !(recs && recs->keep_pages)) CMB_CHECK(cudaEventSynchronize(e->landed[last_buf]));
 		harvest_pending(e, false);
 		return 0;
 	}
@@ -472,8 +474,8 @@ extern "C" int cmb200_put_step(cmb200_engine *e, size_t n, const cmb200_addr *ad
 	std::lock_guard<std::mutex> g(e->mu);
 	CMB_CHECK(cudaSetDevice(e->device));
 	uint64_t t = e->tickets;
-	StepRecords r{rank, (unsigned long long *)records_dev_out};
-	const int rc = n ? put_slice(e, n, addr, valid, (const uint8_t *)pages, pages_on_dev != 0, ts, lens_out, &t, &r) : 0;
+	StepRecords r{rank, (unsigned long long *)records_dev_out, pages_on_dev == 2};
+	const int rc = n ? put_slice(e, n, addr, valid, (const uint8_t *)pages, pages_on_dev == 1, ts, lens_out, &t, &r) : 0;
 	if (ticket) *ticket = t;
 	return rc;
 }

@@ -125,8 +125,10 @@ typedef struct cmb200_stats {
 int cmb200_get_stats(cmb200_engine *e, cmb200_stats *out);
 
 /* One put step of a sharded stream with everything that follows it kept on the device and
- * asynchronous.  Like cmb200_put_batch_async (pages on the host, pages_on_dev = 0) or its
- * device-resident form (pages_on_dev = 1: the pages must stay untouched until the ticket is done),
+ * asynchronous.  Like cmb200_put_batch_async (pages on the host, pages_on_dev = 0), or with the
+ * pages in page-locked host memory that the caller leaves untouched until the ticket is done
+ * (pages_on_dev = 2: the call returns without waiting for its own copies, so the next step can be
+ * queued behind them at once), or device resident (pages_on_dev = 1, same lifetime rule),
  * and additionally writes one 32-byte exchange record per chunk — {u, l, global stream position,
  * rank << 32 | stored length (negative: nothing stored)} — to records_dev_out (device memory,
  * n x 32 bytes) on the engine's stream.  The caller all-gathers those records (NCCL, on that

@@ -548,7 +548,10 @@ def test_put_step_records_and_device_import(E, gpu, oracle):
     valid = np.ones(n, dtype=np.uint8); valid[7] = 0                # rejected address
     base = 1000
     eng.set_stream_order(base + rank, world)
-    for on_dev, src in ((True, d_pages), (False, pages)):
+    hp = E.lib().cmb200_host_alloc(n * 65536)                      # page-locked copy for mode 2
+    pinned = np.ctypeslib.as_array((np.ctypeslib.ctypes.c_uint8 * (n * 65536)).from_address(hp)).reshape(n, 65536)
+    pinned[:] = pages
+    for on_dev, src in ((True, d_pages), (False, pages), (2, pinned)):
         tk = eng.put_step(u, l, src, valid=valid, on_dev=on_dev, rank=rank, records_dev=d_rec)
         eng.wait(tk); eng.sync()
         got = np.zeros((n, 4), dtype=np.int64)
@@ -580,6 +583,7 @@ def test_put_step_records_and_device_import(E, gpu, oracle):
     for p in (d_pages, d_rec, d_rows):
         eng.dev_free(p)
     eng.close()
+    E.lib().cmb200_host_free(hp)
 
 
 def test_arena_compaction_reclaims_deleted_and_outgrown_records(E, gpu, oracle):
