@@ -388,12 +388,12 @@ def run_ours(args):
     stored = float(lens[lens > 0].sum())
     alg_bytes_step = n * (CHUNK + 24 + 64) + stored          # 65 624 + c per chunk
     achieved = alg_bytes_step * args.steps / (enc_ns * 1e-9) / 1e9 if enc_ns else 0.0
-    roofline = {"bound": "hbm", "kernel": "k_encode (fingerprint + LZ4 encode + arena commit)",
+    roofline = {"bound": "hbm", "kernel": "k_encode (LZ4 encode + EF128 fingerprint along the parse + record in place + slot publish)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": peak_src,
                 # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_encode launch of this workload
                 # (16 384 chunks), from the ncu --set full capture summarised in
-                # profiles/r1_encode_notes.md (2.626 GB read + 1.288 GB written); scaled by chunk count
+                # profiles/r1_encode_notes.md (1.357 GB read + 0.647 GB written); scaled by chunk count
                 # if the launch size differs
                 "traffic": 2.003579e9 * (n / max(1, enc_launches // args.steps)) / 16384.0,
                 "traffic_source": "profiles/r1_encode_blend_ncu_details.txt (ncu --set full capture of this launch shape, round 1; not re-measured per run)",
