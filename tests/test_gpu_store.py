@@ -264,7 +264,8 @@ def test_remote_index_import(E, gpu, oracle):
 
 def test_c_caller_links_like_edgefs(E, gpu, tmp_path):
     """A plain C program against include/cachemap.h and -lcachemap (the way edgefs links,
-    Makefile:20,28): async inserts, read-back with byte checks, counters, free."""
+    Makefile:20,28): async inserts, read-back with byte checks, counters, the request-range calls
+    with the glue header, checkpoint, free, and a second cachemap on the same directory."""
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     exe = tmp_path / "drop_in_test"
@@ -272,10 +273,10 @@ def test_c_caller_links_like_edgefs(E, gpu, tmp_path):
     subprocess.run(["gcc", "-std=c99", "-D_DEFAULT_SOURCE", "-O2", "-I", os.path.join(root, "include"),
                     os.path.join(root, "tests", "c", "drop_in_test.c"), "-L", lib_dir, "-lcachemap",
                     f"-Wl,-rpath,{lib_dir}", "-o", str(exe)], check=True)
-    store = tmp_path / "store"
-    store.mkdir()
     env = dict(os.environ, CMB200_ARENA_MB="512", CMB200_MAX_BATCH="512")
     for pshift, n in ((15, 300), (16, 200), (12, 500)):
+        store = tmp_path / f"store{pshift}"
+        store.mkdir()
         out = subprocess.run([str(exe), str(store), str(pshift), str(n)], capture_output=True, text=True, env=env,
                              timeout=200)
         assert out.returncode == 0, (pshift, out.returncode, out.stdout, out.stderr)
