@@ -112,3 +112,22 @@ def test_edgefs_glue_header_matches_oracle(tmp_path, oracle):
         path = b"/" + bytes(rng.integers(1, 256, int(rng.integers(0, 200)), dtype=np.uint8))
         assert L.shim_build_nhid(name, path) == oracle.build_nhid(name, path) \
             == oracle.fnv1a64(name) ^ oracle.fnv1a64(path)
+
+
+def test_snapshot_restatement_roundtrip(tmp_path, oracle):
+    """oracle/snapshot.py (the independent statement of the cache-directory file format used by the
+    GPU tests) writes what it reads: header fields, 16-byte padding, timestamps, record bytes."""
+    import datagen
+    from oracle import snapshot
+    model = oracle.StoreModel(12, 12)
+    recs = []
+    for i, kind in enumerate("RTZMPAXS"):
+        page = datagen.make_page(kind, 4096, 50 + i)
+        model.put(i << 12, 9, 0, page)
+        u, l = oracle.addr_compose(i << 12, 9, 0, 12)
+        recs.append((100 + i, i, ~i & 0xFFFFFFFFFFFFFFFF, model.record_bytes(u, l)))
+    path = str(tmp_path / "s.snap")
+    snapshot.write_snapshot(path, 12, recs, with_fingerprints=True)
+    assert os.path.getsize(path) == 64 + sum(32 + ((len(r[3]) + 15) & ~15) for r in recs)
+    pshift, flags, got = snapshot.read_snapshot(path)
+    assert (pshift, flags, got) == (12, 1, recs)

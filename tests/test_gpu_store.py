@@ -656,3 +656,40 @@ def test_cache_outlives_many_times_its_arena(E, gpu, tmp_path, monkeypatch):
     out, hit = cm.get_batch(off, np.full(100, 3, dtype=np.uint64), np.zeros(100, dtype=np.uint32))
     assert hit.all() and (out == pages[(np.arange(total - 100, total) % 256)]).all()
     cm.free()
+
+
+def test_snapshot_format_against_an_independent_writer_and_reader(E, gpu, oracle, tmp_path):
+    """The snapshot file is a contract of its own: a file written by oracle/snapshot.py from the
+    oracle's store model (records = the reference's LMDB values) loads into the engine and serves
+    the model's pages, and a file written by the engine parses back to exactly the model's records."""
+    from oracle import snapshot
+    n = 400
+    model = oracle.StoreModel(16, 12)
+    pages = [datagen.make_page("RTZMPAXS"[i % 8], 65536, 7000 + i) for i in range(n)]
+    addrs = []
+    for i in range(n):
+        off, nh = (i % 300) << 16, 40 + (i % 2)
+        model.put(off, nh, 0, pages[i])
+        addrs.append(oracle.addr_compose(off, nh, 0, 16))
+    keys = sorted(set(addrs))
+    recs = [(1000 + j, 0, 0, model.record_bytes(u, l)) for j, (u, l) in enumerate(keys)]
+    path = str(tmp_path / "model.snap")
+    snapshot.write_snapshot(path, 16, recs)
+    eng = E.Engine(pshift=16, accel=12, capacity=4096, arena_bytes=256 << 20, max_batch=256)
+    assert eng.load(path) == len(keys) and eng.entries() == model.entries()
+    u = np.array([k[0] for k in keys], dtype=np.uint64)
+    l = np.array([k[1] for k in keys], dtype=np.uint64)
+    assert eng.read_records(u, l) == [r[3] for r in recs]
+    out, status = eng.get(u, l)
+    assert (status == E.HIT).all()
+    for j, (ku, kl) in enumerate(keys):
+        want = model.get(int(kl) << 16, int(ku), 0)          # l = page number (genid 0), u = nhid
+        assert want is not None and bytes(out[j]) == bytes(want), j
+    # and back: what the engine writes is what the independent reader expects
+    path2 = str(tmp_path / "engine.snap")
+    assert eng.save(path2) == len(keys)
+    pshift, flags, got = snapshot.read_snapshot(path2)
+    assert pshift == 16 and flags == 0
+    assert sorted(r[3] for r in got) == sorted(r[3] for r in recs)
+    assert sorted(r[0] for r in got) == sorted(r[0] for r in recs)       # timestamps travel
+    eng.close()
