@@ -395,7 +395,7 @@ def run_ours(args):
                 # (16 384 chunks), from the ncu --set full capture summarised in
                 # profiles/r1_encode_notes.md (1.357 GB read + 0.647 GB written); scaled by chunk count
                 # if the launch size differs
-                "traffic": 2.003579e9 * (n / max(1, enc_launches // args.steps)) / 16384.0,
+                "traffic": 2.004139e9 * (n / max(1, enc_launches // args.steps)) / 16384.0,
                 "traffic_source": "profiles/r1_encode_blend_ncu_details.txt (ncu --set full capture of this launch shape, round 1; not re-measured per run)",
                 "algorithmic_bytes_per_launch": alg_bytes_step / max(1, enc_launches // args.steps),
                 "avg_launch_ms": enc_ns / 1e6 / max(1, enc_launches),
