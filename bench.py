@@ -209,6 +209,26 @@ def workload_config(gpus: int, chunks: int) -> dict:
 # CUDA arm
 # -------------------------------------------------------------------------------------------------
 
+def bind_to_gpu_numa_node(torch, local: int):
+    """Runs this rank on the CPUs next to its GPU (NVML's ideal affinity) so that the page-locked
+    staging buffers it allocates are first-touched on that NUMA node; with 8 ranks on a two-socket
+    host the H2D rate otherwise depends on where the allocator happened to put them.  Returns the
+    previous affinity (restored before the CPU baseline, which uses every host thread)."""
+    try:
+        before = os.sched_getaffinity(0)
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(local).uuid)
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return before
+    except Exception:
+        return None
+
+
 def run_ours(args):
     import torch
     import edge_fuse_b200 as E
@@ -224,6 +244,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     assert E.device_count() > local, f"no CUDA device for rank {rank}: {E.last_error()}"
     torch.cuda.set_device(local)
+    affinity_before = bind_to_gpu_numa_node(torch, local)
 
     n = args.chunks
     total_steps = args.warmup + args.steps
@@ -407,6 +428,8 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         pages_s = h_pages.reshape(n, CHUNK)[: args.cpu_sample_chunks]
+        if affinity_before:
+            os.sched_setaffinity(0, affinity_before)        # the CPU baseline gets every host thread
         r = cpu_reference_run(pages_s, off[: args.cpu_sample_chunks], nh[: args.cpu_sample_chunks],
                               os.cpu_count() or 1)
         key = "put_gibs" if "put_gibs" in r else "codec_encode_gibs"
