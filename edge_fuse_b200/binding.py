@@ -343,7 +343,9 @@ class Engine:
         _check(lib().cmb200_sample(self.h, n, _ptr(r), _ptr(addr), _ptr(ts), _ptr(ok)), "cmb200_sample")
         return addr, ts, ok
 
-    def read_records(self, u, l):
+    def read_records_raw(self, u, l):
+        """-> (records [n, 24 + bsize + 1024] uint8, lens [n] int32; -1 = no record): the stored
+        filemap records {data_prefix, payload} as they lie in the arena."""
         addr = _addr_array(u, l)
         n = len(addr)
         stride = 24 + self.bsize + 1024
@@ -351,7 +353,11 @@ class Engine:
         lens = np.zeros(n, dtype=np.int32)
         _check(lib().cmb200_read_records(self.h, n, _ptr(addr), _ptr(out), stride, _ptr(lens)),
                "cmb200_read_records")
-        return [out[i, :lens[i]].tobytes() if lens[i] >= 0 else None for i in range(n)]
+        return out, lens
+
+    def read_records(self, u, l):
+        out, lens = self.read_records_raw(u, l)
+        return [out[i, :lens[i]].tobytes() if lens[i] >= 0 else None for i in range(len(lens))]
 
     def read_fingerprints(self, u, l):
         addr = _addr_array(u, l)

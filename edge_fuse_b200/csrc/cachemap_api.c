@@ -220,7 +220,10 @@ filemap_drain(struct filemap *m)
 	if (!m->wb_n)
 		return;
 	pthread_mutex_lock(&m->wb_mu);
-	while (m->wb_tail != m->wb_head)
+	/* everything accepted before this call, not "until the ring is empty": with other threads
+	 * still putting the ring may never be empty (the flusher broadcasts after every batch) */
+	const uint64_t target = m->wb_head;
+	while (m->wb_tail < target)
 		pthread_cond_wait(&m->wb_idle, &m->wb_mu);
 	pthread_mutex_unlock(&m->wb_mu);
 }
@@ -256,40 +259,19 @@ filemap_free(struct filemap *m)
 	free(m);
 }
 
-/* Makes room for `incoming` puts: while entries + incoming > capacity, retire the oldest of three
- * random live records (cachemap.c:17-45).  Statistically the reference's policy; bitwise parity
- * is undefined there (wall-clock timestamps, rand()). */
-/* The arena is a bump allocator; when `incoming` more worst-case records would not fit although a
- * good part of it is garbage (deleted and outgrown records), compact it first.  A full arena
- * drops puts, as a full LMDB map does (filemap.c:143-145,154-157). */
-static void
-filemap_check_arena(struct filemap *m, uint64_t incoming)
+/* Retires up to `want` records, each the oldest of three random live ones (cachemap.c:17-45).
+ * Statistically the reference's policy; bitwise parity is undefined there (wall-clock
+ * timestamps, rand()).  Returns how many entries actually went away. */
+static uint64_t
+filemap_evict_n(struct filemap *m, uint64_t want)
 {
-	cmb200_stats st;
-	if (cmb200_get_stats(m->eng, &st) != 0)
-		return;
-	uint64_t need = incoming * ((uint64_t)m->bsize + 1056);
-	if (st.arena_used + need <= st.arena_bytes || st.arena_garbage < st.arena_bytes / 16)
-		return;
-	uint64_t got = 0;
-	if (cmb200_compact(m->eng, &got) != 0)
-		fprintf(stderr, "cachemap_b200: arena compaction failed: %s\n", cmb200_last_error());
-}
-
-static void
-filemap_evict(struct filemap *m, uint64_t incoming)
-{
-	if (!m->capacity)
-		return;
-	for (int round = 0; round < 8; round++) {
-		uint64_t entries = cmb200_entries(m->eng);
-		if (entries + incoming <= m->capacity || entries == 0)
-			return;
-		uint64_t need = entries + incoming - m->capacity;
-		if (need > entries)
-			need = entries;
-		if (need > 1024)
-			need = 1024;    /* per round; the loop continues */
+	uint64_t before = cmb200_entries(m->eng), gone = 0;
+	while (gone < want && before > 0) {
+		uint64_t need = want - gone;
+		if (need > before)
+			need = before;
+		if (need > 4096)
+			need = 4096;    /* per round; the loop continues */
 		uint64_t *draws = malloc(3 * need * sizeof(uint64_t));
 		uint64_t *ts = malloc(3 * need * sizeof(uint64_t));
 		int32_t *ok = malloc(3 * need * sizeof(int32_t));
@@ -311,7 +293,7 @@ filemap_evict(struct filemap *m, uint64_t incoming)
 						pick = (a > c) ? 2 : 0;         /* cachemap.c:29-41 */
 					else
 						pick = (b > c) ? 2 : 1;
-					if (ok[3 * i + pick])
+					if (ok[3 * i + pick] > 0)
 						victim[nv++] = cand[3 * i + pick];
 				}
 				if (nv)
@@ -321,10 +303,74 @@ filemap_evict(struct filemap *m, uint64_t incoming)
 			}
 		}
 		free(draws); free(ts); free(ok); free(cand); free(victim);
-		if (nv == 0)
+		/* two draws may have picked the same victim: count what really left the table */
+		uint64_t after = cmb200_entries(m->eng);
+		if (nv == 0 || after >= before)
+			break;          /* no progress */
+		gone += before - after;
+		before = after;
+	}
+	return gone;
+}
+
+/* Before `incoming` puts: while entries + incoming > capacity, evict (cachemap.c:17-45); loops
+ * until the count fits or nothing more can be retired. */
+static void
+filemap_evict(struct filemap *m, uint64_t incoming)
+{
+	if (!m->capacity)
+		return;
+	for (;;) {
+		uint64_t entries = cmb200_entries(m->eng);
+		if (entries + incoming <= m->capacity || entries == 0)
 			return;
+		uint64_t need = entries + incoming - m->capacity;
 		if (incoming == 1)
-			return;         /* the reference evicts exactly one per put */
+			need = 1;       /* the reference evicts exactly one per put */
+		if (filemap_evict_n(m, need) == 0 || incoming == 1)
+			return;
+	}
+}
+
+/* The arena is a bump allocator; deleted and outgrown records stay behind as garbage until
+ * cmb200_compact slides the live ones down.  When `incoming` worst-case records would not fit:
+ * compact if that frees enough; otherwise the live data itself fills the arena (the store was
+ * sized in pages, the arena is bytes), so evict by bytes as well and compact what that frees.
+ * Only when even that fails does a put get dropped, as a full LMDB map drops it
+ * (filemap.c:143-145,154-157). */
+static void
+filemap_check_arena(struct filemap *m, uint64_t incoming)
+{
+	const uint64_t need = incoming * ((uint64_t)m->bsize + 1056);
+	int evicted = 0;
+	for (int attempt = 0; attempt < 6; attempt++) {
+		cmb200_stats st;
+		if (cmb200_get_stats(m->eng, &st) != 0)
+			return;
+		if (st.arena_used + need <= st.arena_bytes)
+			return;
+		const uint64_t free_b = st.arena_bytes - st.arena_used;
+		if (st.arena_garbage > 0 && (free_b + st.arena_garbage >= need || evicted)) {
+			uint64_t got = 0;
+			if (cmb200_compact(m->eng, &got) != 0) {
+				fprintf(stderr, "cachemap_b200: arena compaction failed: %s\n", cmb200_last_error());
+				return;
+			}
+			evicted = 0;
+			continue;
+		}
+		if (st.entries == 0)
+			return;
+		/* live records fill the arena: retire enough of them (average record size, plus a margin) */
+		const uint64_t live = st.arena_used > st.arena_garbage ? st.arena_used - st.arena_garbage : 1;
+		const uint64_t avg = live / st.entries ? live / st.entries : 1;
+		const uint64_t shortfall = need - (free_b + st.arena_garbage < need ? free_b + st.arena_garbage : need);
+		uint64_t victims = shortfall / avg + shortfall / avg / 8 + 16;
+		if (victims > st.entries)
+			victims = st.entries;
+		if (filemap_evict_n(m, victims) == 0)
+			return;
+		evicted = 1;
 	}
 }
 
@@ -396,8 +442,7 @@ filemap_flusher(void *arg)
 			m->wb_slot[(m->wb_tail + i) % m->wb_n].state = WB_FREE;
 		m->wb_tail += count;
 		pthread_cond_broadcast(&m->wb_space);
-		if (m->wb_tail == m->wb_head)
-			pthread_cond_broadcast(&m->wb_idle);
+		pthread_cond_broadcast(&m->wb_idle);            /* waiters compare wb_tail with their own target */
 	}
 	pthread_mutex_unlock(&m->wb_mu);
 	free(addr);
@@ -746,15 +791,31 @@ put_batch_common(struct cachemap *cm, uint64_t n, const uint64_t *offset, const 
 	if (batch_keys_build(cm, n, offset, nhid, genid, 1, &bk) != 0)
 		return;
 	filemap_drain(cm->pages);               /* earlier single puts land first */
-	filemap_make_room(cm->pages, n);
 	__atomic_fetch_add(&cm->pages->puts_seen, n, __ATOMIC_RELAXED);
-	if (on_dev)
-		cmb200_put_batch_dev(cm->pages->eng, (size_t)n, bk.addr, bk.valid, pages, bk.ts, NULL);
-	else {
-		/* write-behind like cachemap_put: back when the pages have crossed to the GPU and the
-		 * caller may reuse them; whatever is called next is ordered after the encode */
-		uint64_t ticket;
-		cmb200_put_batch_async(cm->pages->eng, (size_t)n, bk.addr, bk.valid, pages, bk.ts, NULL, &ticket);
+	/* One GPU batch when the store has room for all of it; at capacity the batch goes in slices
+	 * with eviction before each, so that entries never run past capacity by more than a slice
+	 * (the reference evicts before every single put, cachemap.c:186-197). */
+	uint64_t slice = n;
+	if (cm->capacity && cmb200_entries(cm->pages->eng) + n > cm->capacity) {
+		slice = cm->capacity / 4;
+		if (slice > 4096)
+			slice = 4096;
+		if (slice < 1)
+			slice = 1;
+	}
+	const size_t bsize = (size_t)cm->pages->bsize;
+	for (uint64_t at = 0; at < n; at += slice) {
+		const uint64_t m = n - at < slice ? n - at : slice;
+		const uint8_t *pg = (const uint8_t *)pages + at * bsize;
+		filemap_make_room(cm->pages, m);
+		if (on_dev)
+			cmb200_put_batch_dev(cm->pages->eng, (size_t)m, bk.addr + at, bk.valid + at, pg, bk.ts + at, NULL);
+		else {
+			/* write-behind like cachemap_put: back when the pages have crossed to the GPU and the
+			 * caller may reuse them; whatever is called next is ordered after the encode */
+			uint64_t ticket;
+			cmb200_put_batch_async(cm->pages->eng, (size_t)m, bk.addr + at, bk.valid + at, pg, bk.ts + at, NULL, &ticket);
+		}
 	}
 	batch_keys_free(&bk);
 }

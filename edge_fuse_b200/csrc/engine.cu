@@ -53,6 +53,8 @@ struct cmb200_engine {
 	int32_t *d_lens = nullptr, *d_status = nullptr;
 	uint64_t *d_fps = nullptr, *d_recoff = nullptr;
 	unsigned int *d_work = nullptr;
+	uint32_t *d_import_slot = nullptr;   // slot scratch of cmb200_import_records_dev
+	size_t import_slot_cap = 0;
 	// page-locked staging for the small per-chunk arrays, so that no copy ever blocks the host
 	// thread that is feeding the pipeline (a pageable cudaMemcpyAsync waits for the stream)
 	static constexpr size_t META_CAP = 1u << 18;   // chunks per outer slice of a call
@@ -118,7 +120,7 @@ extern "C" void cmb200_engine_destroy(cmb200_engine *e) {
 	cudaFree(e->d_pages[0]); cudaFree(e->d_pages[1]); cudaFree(e->d_stage);
 	cudaFree(e->d_addr); cudaFree(e->d_ts); cudaFree(e->d_valid); cudaFree(e->d_slot); cudaFree(e->d_vlen);
 	if (e->h_meta) cudaFreeHost(e->h_meta);
-	cudaFree(e->d_lens); cudaFree(e->d_status); cudaFree(e->d_fps); cudaFree(e->d_recoff); cudaFree(e->d_work);
+	cudaFree(e->d_lens); cudaFree(e->d_status); cudaFree(e->d_fps); cudaFree(e->d_recoff); cudaFree(e->d_work); cudaFree(e->d_import_slot);
 	for (int i = 0; i < 2; i++) {
 		if (e->landed[i]) cudaEventDestroy(e->landed[i]);
 		if (e->consumed[i]) cudaEventDestroy(e->consumed[i]);
@@ -223,7 +225,10 @@ extern "C" cmb200_engine *cmb200_engine_create(const cmb200_config *cfg) {
 		if (!arena) {
 			size_t free_b = 0, total_b = 0;
 			ENG_CHECK(cudaMemGetInfo(&free_b, &total_b));
+			// capacity worst-case records (incompressible pages: 24 + bsize + bsize/255 + 16) plus 1/8
+			// headroom, so that a store at capacity still has garbage worth compacting
 			uint64_t want = (cfg->capacity ? cfg->capacity : 1024) * (e->stage_stride + 32);
+			want += want / 8;
 			uint64_t lim = (uint64_t)(free_b * 0.8);
 			arena = want < lim ? want : lim;
 		}
@@ -483,12 +488,19 @@ extern "C" int cmb200_put_step(cmb200_engine *e, size_t n, const cmb200_addr *ad
 extern "C" int cmb200_import_records_dev(cmb200_engine *e, size_t n_total, const void *records_dev, uint32_t my_rank) {
 	std::lock_guard<std::mutex> g(e->mu);
 	CMB_CHECK(cudaSetDevice(e->device));
-	const unsigned long long *rec = (const unsigned long long *)records_dev;
-	for (size_t at = 0; at < n_total; at += e->max_batch) {
-		const uint32_t m = (uint32_t)((n_total - at < e->max_batch) ? n_total - at : e->max_batch);
-		if (launch_import_records(e->table, e->arena, rec + 4 * at, m, my_rank, e->d_slot, e->st)) return -1;
-		e->stats.kernel_launches += 2;
+	if (n_total == 0) return 0;
+	if (n_total > 0xffffffffull) { set_error_msg("cmb200_import_records_dev: too many records"); return -1; }
+	// the whole gathered buffer in one claim + one apply launch (the slot scratch grows on demand)
+	if (n_total > e->import_slot_cap) {
+		CMB_CHECK(cudaStreamSynchronize(e->st));
+		if (e->d_import_slot) cudaFree(e->d_import_slot);
+		e->d_import_slot = nullptr; e->import_slot_cap = 0;
+		CMB_CHECK(cudaMalloc(&e->d_import_slot, n_total * sizeof(uint32_t)));
+		e->import_slot_cap = n_total;
 	}
+	if (launch_import_records(e->table, e->arena, (const unsigned long long *)records_dev, (uint32_t)n_total, my_rank,
+		e->d_import_slot, e->st)) return -1;
+	e->stats.kernel_launches += 2;
 	return 0;                                               // asynchronous: ordered on the engine's stream
 }
 
@@ -664,7 +676,9 @@ extern "C" int cmb200_get_stats(cmb200_engine *e, cmb200_stats *out) {
 	if (read_counters(e, c)) return -1;
 	harvest_pending(e, true);
 	*out = e->stats;
-	out->entries = c[0]; out->tombstones = c[1]; out->arena_used = c[2]; out->arena_garbage = c[3];
+	out->entries = c[0]; out->tombstones = c[1];
+	out->arena_used = c[2] < e->arena.size ? c[2] : e->arena.size;   // the bump pointer saturates past the end (no rollback)
+	out->arena_garbage = c[3];
 	out->dropped_puts = c[4]; out->remote_entries = c[5];
 	out->table_slots = e->table.cap; out->arena_bytes = e->arena.size;
 	return 0;
@@ -847,6 +861,13 @@ extern "C" int cmb200_load(cmb200_engine *e, const char *path, uint64_t *records
 			if (r.len < 24 || r.len > 24u + e->bsize + 1024u) { rc = -1; break; }
 			if (used + padded > blob_cap) { pending = r; have_pending = true; break; }
 			if (fread(blob + used, padded, 1, f) != 1) { rc = -1; break; }
+			{
+				// the record must be what filemap_set would have stored (filemap.c:124-147): a foreign or
+				// corrupt file must not reach k_restore, which trusts compressed_length
+				int32_t clen;
+				memcpy(&clen, blob + used + 16, 4);
+				if (clen < 0 || (uint32_t)clen > e->bsize + 1024u || r.len != 24u + (clen ? (uint32_t)clen : e->bsize)) { rc = -1; break; }
+			}
 			memcpy(&addr[m], blob + used, 16);      // data_prefix {u, l}
 			off[m] = used; ts[m] = r.ts; fps[2 * m] = r.fp_hi; fps[2 * m + 1] = r.fp_lo;
 			used += padded; m++;

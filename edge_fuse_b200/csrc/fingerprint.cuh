@@ -26,6 +26,18 @@ __device__ __forceinline__ uint64_t ef_av(uint64_t h) {
 
 struct EfLane { uint64_t a, b, s0, s1, s2, s3; };
 
+// 16-byte page load of the fingerprint pass.  Every page byte is absorbed exactly once, so in the
+// fused encoder the stripes are pure streaming traffic: NOALLOC keeps them out of the L1, which the
+// parse needs for its match-candidate reads (ld.global.nc.L1::no_allocate).
+template <bool NOALLOC> __device__ __forceinline__ uint4 ef_ld16(const uint4 *p) {
+	if (NOALLOC) {
+		uint4 v;
+		asm("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+		return v;
+	}
+	return __ldg(p);
+}
+
 __device__ __forceinline__ void ef_init(EfLane &L, int lane) {
 	L.s0 = ef_secret(4 * lane); L.s1 = ef_secret(4 * lane + 1);
 	L.s2 = ef_secret(4 * lane + 2); L.s3 = ef_secret(4 * lane + 3);
@@ -89,7 +101,7 @@ __device__ __forceinline__ void warp_fingerprint128(const uint8_t *src, uint32_t
 // are absorbed in order as the caller's position advances, one stripe requested ahead of need, so
 // the page crosses HBM once and the stripe loads double as a prefetch for the parse that follows
 // them.  Same result as warp_fingerprint128.
-struct EfFrontier {
+template <bool NOALLOC = false> struct EfFrontierT {
 	EfLane L;
 	uint4 ahead;          // stripe `next`, already requested
 	uint32_t next;        // next stripe to absorb
@@ -99,7 +111,7 @@ struct EfFrontier {
 		ef_init(L, lane);
 		next = 0;
 		full = n >> 9;
-		ahead = full ? __ldg(reinterpret_cast<const uint4 *>(src) + lane) : make_uint4(0, 0, 0, 0);
+		ahead = full ? ef_ld16<NOALLOC>(reinterpret_cast<const uint4 *>(src) + lane) : make_uint4(0, 0, 0, 0);
 	}
 	__device__ __forceinline__ void take(const uint4 &x) {
 		ef_absorb(L, (uint64_t)x.x | ((uint64_t)x.y << 32), (uint64_t)x.z | ((uint64_t)x.w << 32));
@@ -114,19 +126,19 @@ struct EfFrontier {
 		take(ahead);
 		// a long match jumped ahead: single stripes up to a scramble boundary, then 16 stripes per
 		// step with 16 loads in flight, then the remainder
-		while (next < target && (next & 15u)) { const uint4 x = __ldg(v + (size_t)next * 32); take(x); }
+		while (next < target && (next & 15u)) { const uint4 x = ef_ld16<NOALLOC>(v + (size_t)next * 32); take(x); }
 		while (target - next >= 16u) {
 			uint4 x[16];
 #pragma unroll
-			for (int k = 0; k < 16; k++) x[k] = __ldg(v + (size_t)(next + k) * 32);
+			for (int k = 0; k < 16; k++) x[k] = ef_ld16<NOALLOC>(v + (size_t)(next + k) * 32);
 #pragma unroll
 			for (int k = 0; k < 16; k++)
 				ef_absorb(L, (uint64_t)x[k].x | ((uint64_t)x[k].y << 32), (uint64_t)x[k].z | ((uint64_t)x[k].w << 32));
 			ef_scramble(L);
 			next += 16;
 		}
-		while (next < target) { const uint4 x = __ldg(v + (size_t)next * 32); take(x); }
-		if (next < full) ahead = __ldg(v + (size_t)next * 32);
+		while (next < target) { const uint4 x = ef_ld16<NOALLOC>(v + (size_t)next * 32); take(x); }
+		if (next < full) ahead = ef_ld16<NOALLOC>(v + (size_t)next * 32);
 	}
 	// absorb the rest of the page (incl. a zero-padded partial stripe) and fold the lanes
 	__device__ __forceinline__ void finish(const uint8_t *src, uint32_t n, int lane, uint64_t &hi, uint64_t &lo) {
@@ -151,5 +163,6 @@ struct EfFrontier {
 		hi = ef_av(~((uint64_t)n * 0xC2B2AE3D27D4EB4FULL) + w);
 	}
 };
+typedef EfFrontierT<false> EfFrontier;
 
 }  // namespace cmb

@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "fingerprint.cuh"
 #include "lz4_encode.cuh"
+#include "lz4_encode_ring.cuh"
 #include "lz4_encode_groups.cuh"
 #include <type_traits>
 #include "lz4_decode.cuh"
@@ -180,22 +181,60 @@ __global__ void k_unset(TableView t, ArenaView a, const unsigned long long *addr
 	}
 }
 
+// filemap_get_rand (filemap.c:264-314) picks the first key at or after a random 64-bit draw; the
+// policy-equivalent here is the first live slot at or after a random slot.  One thread per draw
+// walks at most SAMPLE_WALK slots (a table at its eviction threshold is >= 1/8 full, so this
+// almost always ends within a few slots) and redraws a few times; whatever is still unresolved
+// (a nearly empty table) is finished by k_sample_scan, one CTA per draw, 256 slots per step.
+constexpr uint32_t SAMPLE_WALK = 128, SAMPLE_REDRAWS = 8;
+__device__ __forceinline__ bool slot_live(const Slot &s) { return s.vlen != 0; }
 __global__ void k_sample(TableView t, const unsigned long long *r, uint32_t n, unsigned long long *addr_out,
     unsigned long long *ts_out, int32_t *ok) {
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
-	uint64_t start = home_slot(r[i], t.cap);
-	int32_t found = 0;
-	for (uint64_t k = 0; k < t.cap + 2; k++) {
-		uint64_t j = (start + k) % (t.cap + 2);
-		const Slot &s = t.slots[j];
-		if (s.vlen != 0) {
-			addr_out[2 * i] = s.addr_u; addr_out[2 * i + 1] = s.addr_l; ts_out[i] = s.ts;
-			found = 1;
-			break;
+	unsigned long long draw = r[i];
+	int32_t found = -1;                                   // -1 = left to k_sample_scan
+	for (uint32_t a = 0; a < SAMPLE_REDRAWS && found < 0; a++) {
+		const uint64_t start = home_slot(draw, t.cap);
+		for (uint32_t k = 0; k < SAMPLE_WALK; k++) {
+			const uint64_t j = (start + k) % (t.cap + 2);
+			const Slot &s = t.slots[j];
+			if (slot_live(s)) {
+				addr_out[2 * i] = s.addr_u; addr_out[2 * i + 1] = s.addr_l; ts_out[i] = s.ts;
+				found = 1;
+				break;
+			}
 		}
+		draw = draw * 0x9E3779B97F4A7C15ULL + 0xD1B54A32D192ED03ULL;
 	}
 	ok[i] = found;
+}
+__global__ void __launch_bounds__(256) k_sample_scan(TableView t, const unsigned long long *r, uint32_t n,
+    unsigned long long *addr_out, unsigned long long *ts_out, int32_t *ok) {
+	__shared__ unsigned long long first;
+	for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
+		if (ok[i] >= 0) continue;                         // uniform across the CTA
+		const uint64_t total = t.cap + 2, start = home_slot(r[i], t.cap);
+		if (threadIdx.x == 0) first = ~0ull;
+		__syncthreads();
+		for (uint64_t base = 0; base < total; base += blockDim.x) {
+			const uint64_t k = base + threadIdx.x;
+			if (k < total && slot_live(t.slots[(start + k) % total])) atomicMin(&first, (unsigned long long)k);
+			__syncthreads();
+			if (first != ~0ull) break;
+			__syncthreads();
+		}
+		if (threadIdx.x == 0) {
+			if (first != ~0ull) {
+				const Slot &s = t.slots[(start + first) % total];
+				addr_out[2 * i] = s.addr_u; addr_out[2 * i + 1] = s.addr_l; ts_out[i] = s.ts;
+				ok[i] = 1;
+			} else {
+				ok[i] = 0;
+			}
+		}
+		__syncthreads();
+	}
 }
 
 // ------------------------------------------------------------------------------------------
@@ -218,8 +257,9 @@ __device__ void commit_record(const EncodeJob &job, uint32_t i, uint32_t idx, co
 			off = atomicAdd(job.arena.head, (unsigned long long)need);
 			if (off + need > job.arena.size) {
 				// arena full: the put is dropped silently, as a full LMDB map drops it
-				// (filemap.c:143-145,154-157).
-				atomicAdd(job.arena.head, (unsigned long long)-(long long)need);
+				// (filemap.c:143-145,154-157).  The bump pointer is never rolled back (a rollback
+				// races with allocations that succeeded in between and would hand their bytes out
+				// twice): it stays saturated until cmb200_compact resets it.
 				atomicAdd(job.arena.dropped, 1ull);
 				if (s.vlen) atomicAdd(job.table.entries, (unsigned long long)-1ll);
 				s.vlen = 0; s.alloc = 0;
@@ -298,11 +338,19 @@ __device__ uint32_t commit_direct(const EncodeJob &job, uint32_t i, uint32_t idx
 	return reuse ? 0u : need;
 }
 
-template <bool WIDE>
+// ENC 0: page read through the L1 (lz4_encode.cuh).  ENC 1: parse frontier staged in a per-warp
+// shared-memory ring by TMA (lz4_encode_ring.cuh); shared memory = tables | rings | mbarriers.
+// FPNA: the fingerprint's streaming loads do not allocate in the L1.
+template <bool WIDE, int ENC, bool FPNA>
 __global__ void __launch_bounds__(512, 1) k_encode(EncodeJob job) {
-	extern __shared__ __align__(16) uint8_t smem[];
+	extern __shared__ __align__(128) uint8_t smem[];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint32_t nwarps = blockDim.x >> 5;
 	uint8_t *wsm = smem + (size_t)warp * LZ4_TABLE_BYTES;
+	PageRing ring;
+	if (ENC == 1)
+		ring_setup(ring, smem + (size_t)nwarps * LZ4_TABLE_BYTES + (size_t)warp * RING_BYTES,
+		    smem + (size_t)nwarps * (LZ4_TABLE_BYTES + RING_BYTES) + (size_t)warp * RING_MBAR_BYTES, lane);
 	const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + warp;         // resident warp slot
 	const bool direct = job.slot_idx != nullptr && job.arena.seg_bytes != 0u && job.accel != 0u && gw < ARENA_SEG_SLOTS;
 	// room one chunk may need while it is being encoded: prefix + a stage row (filemap.c:120 dest[bsize+1024])
@@ -345,7 +393,7 @@ __global__ void __launch_bounds__(512, 1) k_encode(EncodeJob job) {
 					if (seg_end > seg_cur) atomicAdd(job.arena.garbage, seg_end - seg_cur);
 					const unsigned long long off = atomicAdd(job.arena.head, (unsigned long long)job.arena.seg_bytes);
 					if (off + job.arena.seg_bytes <= job.arena.size) { seg_cur = off; seg_end = off + job.arena.seg_bytes; }
-					else { atomicAdd(job.arena.head, (unsigned long long)-(long long)job.arena.seg_bytes); seg_cur = seg_end = 0; }
+					else { seg_cur = seg_end = 0; }       // no rollback (see commit_record): saturated until compaction
 				}
 				in_arena = seg_cur + worst <= seg_end;
 				base = seg_cur;
@@ -356,10 +404,12 @@ __global__ void __launch_bounds__(512, 1) k_encode(EncodeJob job) {
 		}
 		uint32_t clen;
 		if (job.fps) {                  // fingerprint along the parse frontier: the page is read once
-			clen = lz4_encode_warp<WIDE, true>(src, job.nbytes, dst, job.accel, wsm, lane, fp_hi, fp_lo);
+			if (ENC == 1) clen = lz4_encode_ring<WIDE, true, FPNA>(src, job.nbytes, dst, job.accel, wsm, ring, lane, fp_hi, fp_lo);
+			else clen = lz4_encode_warp<WIDE, true, FPNA>(src, job.nbytes, dst, job.accel, wsm, lane, fp_hi, fp_lo);
 			if (lane == 0) { job.fps[2 * (size_t)i] = fp_hi; job.fps[2 * (size_t)i + 1] = fp_lo; }
 		} else {
-			clen = lz4_encode_warp<WIDE, false>(src, job.nbytes, dst, job.accel, wsm, lane, fp_hi, fp_lo);
+			if (ENC == 1) clen = lz4_encode_ring<WIDE, false, false>(src, job.nbytes, dst, job.accel, wsm, ring, lane, fp_hi, fp_lo);
+			else clen = lz4_encode_warp<WIDE, false, false>(src, job.nbytes, dst, job.accel, wsm, lane, fp_hi, fp_lo);
 		}
 		if (lane == 0) job.lens[i] = (int32_t)clen;
 		if (store) {
@@ -394,8 +444,7 @@ __device__ void grp_commit_record(const GroupCtx &g, const EncodeJob &job, uint3
 			if (s.alloc) atomicAdd(job.arena.garbage, (unsigned long long)s.alloc);
 			off = atomicAdd(job.arena.head, (unsigned long long)need);
 			if (off + need > job.arena.size) {
-				atomicAdd(job.arena.head, (unsigned long long)-(long long)need);
-				atomicAdd(job.arena.dropped, 1ull);
+				atomicAdd(job.arena.dropped, 1ull);      // no rollback, see commit_record
 				if (s.vlen) atomicAdd(job.table.entries, (unsigned long long)-1ll);
 				s.vlen = 0; s.alloc = 0;
 				ok = 0;
@@ -610,18 +659,13 @@ static int launch_encode_groups(const EncodeJob &job_in, cudaStream_t st, bool z
 	return 0;
 }
 
-static int launch_encode_warps(const EncodeJob &job, cudaStream_t st) {
-	// Residency is bounded by shared memory: one 16 KiB position table per chunk, 14 of them in
-	// the 227 KiB of an SM (2 CTAs x 7 warps); grid = 2 CTAs per SM, chunks handed out dynamically.
-	static int warps = env_int("CMB200_ENC_WARPS", 7, 1, 14);
-	static int ctas = env_int("CMB200_ENC_CTAS_PER_SM", 2, 1, 8);
-	size_t smem = (size_t)warps * LZ4_TABLE_BYTES;
-	auto kern = job.nbytes >= LZ4_NARROW_LIMIT ? k_encode<true> : k_encode<false>;
+template <class K>
+static int launch_encode_kernel(K kern, const EncodeJob &job, int warps, int ctas_per_sm, size_t smem, cudaStream_t st) {
 	CMB_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	// what the tables leave of the 256 KiB per SM is L1 for the page reads; -1 = driver's choice
 	static int carve = env_int("CMB200_ENC_CARVEOUT", -1, -1, 100);
 	if (carve >= 0) CMB_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-	uint32_t grid = (uint32_t)(sm_count() * ctas);
+	uint32_t grid = (uint32_t)(sm_count() * ctas_per_sm);
 	uint32_t need = (job.n + warps - 1) / warps;
 	if (grid > need) grid = need;
 	kern<<<grid, warps * 32, smem, st>>>(job);
@@ -629,18 +673,46 @@ static int launch_encode_warps(const EncodeJob &job, cudaStream_t st) {
 	return 0;
 }
 
+// Plain organisation: residency is bounded by shared memory, one 16 KiB position table per chunk,
+// 14 of them in the 227 KiB of an SM (2 CTAs x 7 warps); chunks handed out dynamically.
+static int launch_encode_warps(const EncodeJob &job, cudaStream_t st, bool fpna) {
+	static int warps = env_int("CMB200_ENC_WARPS", 7, 1, 14);
+	static int ctas = env_int("CMB200_ENC_CTAS_PER_SM", 2, 1, 8);
+	const size_t smem = (size_t)warps * LZ4_TABLE_BYTES;
+	const bool wide = job.nbytes >= LZ4_NARROW_LIMIT;
+	if (wide) return fpna ? launch_encode_kernel(k_encode<true, 0, true>, job, warps, ctas, smem, st)
+	                      : launch_encode_kernel(k_encode<true, 0, false>, job, warps, ctas, smem, st);
+	return fpna ? launch_encode_kernel(k_encode<false, 0, true>, job, warps, ctas, smem, st)
+	            : launch_encode_kernel(k_encode<false, 0, false>, job, warps, ctas, smem, st);
+}
+
+// Ring organisation (lz4_encode_ring.cuh): table + 1 KiB TMA ring + mbarriers per warp, 13 chunks
+// per SM in one CTA.
+static int launch_encode_ring(const EncodeJob &job, cudaStream_t st, bool fpna) {
+	static int warps = env_int("CMB200_RING_WARPS", 13, 1, 13);
+	const size_t smem = (size_t)warps * RING_WARP_SMEM;
+	const bool wide = job.nbytes >= LZ4_NARROW_LIMIT;
+	if (wide) return fpna ? launch_encode_kernel(k_encode<true, 1, true>, job, warps, 1, smem, st)
+	                      : launch_encode_kernel(k_encode<true, 1, false>, job, warps, 1, smem, st);
+	return fpna ? launch_encode_kernel(k_encode<false, 1, true>, job, warps, 1, smem, st)
+	            : launch_encode_kernel(k_encode<false, 1, false>, job, warps, 1, smem, st);
+}
+
 int launch_encode(const EncodeJob &job_in, cudaStream_t st) {
 	if (job_in.n == 0) return 0;
 	// Two organisations of the same encoder (identical output).
 	//   0 "warps":  one warp per chunk, position table in shared memory — lowest latency per
 	//               chunk, 14 chunks per SM.  Default: best on mixed batches and small launches.
+	//   2 "ring":   "warps" with the parse frontier staged in a per-warp shared-memory ring by TMA
+	//               (lz4_encode_ring.cuh), 13 chunks per SM.  Default.
 	//   1 "groups": one 8-lane group per chunk, table in global memory, 96 chunks per SM — bound by
 	//               L2/HBM latency instead of shared-memory residency; ~15 % faster on match-heavy
 	//               pages in 16 Ki-chunk launches, slower on incompressible ones and small launches.
 	// Running both at once on one batch (shared chunk counter, two streams) was measured too: the
 	// SM does not add the two up (profiles/r1_encode_notes.md).
-	static int mode = env_int("CMB200_ENC_MODE", 0, 0, 1);
+	static int mode = env_int("CMB200_ENC_MODE", 0, 0, 2);
 	static int grp_ctas = env_int("CMB200_GRP_CTAS_PER_SM", 6, 1, 6);
+	static int fpna = env_int("CMB200_FP_NOALLOC", 0, 0, 1);
 	EncodeJob job = job_in;
 	if (mode == 1) {
 		// the fingerprint is fused into the warp kernel; the group kernel takes it from a pass before
@@ -648,7 +720,11 @@ int launch_encode(const EncodeJob &job_in, cudaStream_t st) {
 		return launch_encode_groups(job, st, true, grp_ctas);
 	}
 	CMB_CHECK(cudaMemsetAsync(job.work, 0, sizeof(unsigned int), st));
-	return launch_encode_warps(job, st);
+	// the ring holds what 30 probes at accel <= 12 reach and TMA wants 16-byte aligned pages
+	const bool ring_ok = job.accel >= 1 && job.accel <= RING_MAX_ACCEL && job.nbytes < (1u << 24) &&
+	    (reinterpret_cast<uintptr_t>(job.pages) & 15u) == 0 && (job.page_stride & 15u) == 0;
+	if (mode == 2 && ring_ok) return launch_encode_ring(job, st, fpna != 0);
+	return launch_encode_warps(job, st, fpna != 0);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -953,6 +1029,8 @@ int launch_sample(TableView t, const unsigned long long *r, uint32_t n, unsigned
     unsigned long long *ts_out, int32_t *ok, cudaStream_t st) {
 	if (n == 0) return 0;
 	k_sample<<<GRID1D(n), 0, st>>>(t, r, n, addr_out, ts_out, ok);
+	CMB_CHECK(cudaGetLastError());
+	k_sample_scan<<<n < 1024u ? n : 1024u, 256, 0, st>>>(t, r, n, addr_out, ts_out, ok);
 	CMB_CHECK(cudaGetLastError());
 	return 0;
 }

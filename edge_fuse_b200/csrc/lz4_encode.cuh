@@ -171,9 +171,11 @@ __device__ __forceinline__ uint64_t lz4_pack(bool found, bool retest, uint32_t i
 
 // The general search (any number of probes, any hash clashes).  Slot g of the search is the
 // refill (g = 0) / re-test (g = 1) when g < shift, else probe g - shift; starts at slot g0.
+// specials = false: the two special slots exist in the numbering but do nothing (first search of
+// a chunk in the ring encoder, which keeps one lane layout for every batch).
 template <bool WIDE>
 __device__ __noinline__ uint64_t lz4_search_slow(const uint8_t *src, uint32_t lim4, Lz4Table<WIDE> tab,
-    uint32_t anchor, uint32_t shift, uint32_t accel, uint32_t mflimit, uint32_t g0, int lane) {
+    uint32_t anchor, uint32_t shift, uint32_t accel, uint32_t mflimit, uint32_t g0, int lane, bool specials = true) {
 	const uint32_t p0 = anchor + 1;
 	for (;; g0 += 32) {
 		const uint32_t g = g0 + lane;
@@ -182,7 +184,7 @@ __device__ __noinline__ uint64_t lz4_search_slow(const uint8_t *src, uint32_t li
 		uint32_t pos = p0 + lz4_probe_off(k, accel);
 		const uint32_t nxt = p0 + lz4_probe_off(k + 1, accel);
 		bool en = nxt <= mflimit;
-		if (special) { pos = anchor - 2u + 2u * g; en = true; }
+		if (special) { pos = anchor - 2u + 2u * g; en = specials; }
 		uint32_t h = 0x10000u + lane, pseq = 0, cand = 0;
 		if (en) {
 			if (WIDE) { uint64_t v = read64u(src, pos, lim4); pseq = (uint32_t)v; h = lz4_hash5(v); }
@@ -199,7 +201,7 @@ __device__ __noinline__ uint64_t lz4_search_slow(const uint8_t *src, uint32_t li
 		const uint32_t hits = __ballot_sync(CMB_FULL, hit);
 		const uint32_t enmask = __ballot_sync(CMB_FULL, en);
 		const int w = hits ? __ffs(hits) - 1 : 31;
-		const uint32_t commit = hits ? (0xffffffffu >> (31 - w)) : enmask;
+		const uint32_t commit = hits ? (0xffffffffu >> (31 - w)) & enmask : enmask;
 		if ((commit >> lane) & 1u) {
 			const uint32_t pc = peers & commit;
 			if (31 - __clz(pc) == lane) tab.put(h, pos);     // last writer per slot wins
@@ -208,7 +210,7 @@ __device__ __noinline__ uint64_t lz4_search_slow(const uint8_t *src, uint32_t li
 		if (hits)
 			return lz4_pack(true, g0 + (uint32_t)w < shift, __shfl_sync(CMB_FULL, pos, w),
 			    __shfl_sync(CMB_FULL, cand, w));
-		if (enmask != CMB_FULL) return 0;
+		if (__ballot_sync(CMB_FULL, en || special) != CMB_FULL) return 0;   // a probe ran into the end margin
 	}
 }
 
@@ -234,14 +236,14 @@ __device__ __noinline__ uint32_t lz4_emit_general(uint8_t *dst, uint32_t op, con
 // readable up to 16 bytes past src+n (the library's page buffers are contiguous and padded).
 // With FP the EF128 fingerprint of the page is computed along the way (EfFrontier): the parse and
 // the fingerprint then read the page from HBM once, and the stripe loads prefetch the parse.
-template <bool WIDE, bool FP>
+template <bool WIDE, bool FP, bool FP_NOALLOC = false>
 __device__ uint32_t lz4_encode_warp(const uint8_t *__restrict__ src, uint32_t n, uint8_t *__restrict__ dst,
     uint32_t accel, uint8_t *smem, int lane, uint64_t &fp_hi, uint64_t &fp_lo) {
 	Lz4Table<WIDE> tab;
 	tab.t = reinterpret_cast<decltype(tab.t)>(smem);
 	const uint32_t lim4 = (n + 3u) & ~3u;
 	uint32_t op = 0, anchor = 0;
-	EfFrontier fp;
+	EfFrontierT<FP_NOALLOC> fp;
 	if (FP) fp.start(src, n, lane);
 
 	// lz4.c:739 — table cleared per call: an untouched slot aliases position 0.

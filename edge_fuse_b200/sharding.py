@@ -96,3 +96,101 @@ def import_gathered(engine, gathered, rank: int) -> int:
         a = addr.numpy().view(np.uint64)
         engine.import_remote(a[:, 0], a[:, 1], owner.numpy().view(np.uint32), seq.numpy().view(np.uint64))
     return n
+
+
+class StepExchange:
+    """The sharded put step as the product runs it (SURVEY.md §8e option B), device resident:
+
+        engine stream   put_step(k)  [upsert, encode, pack records] | import(k-1) | put_step(k+1) | ...
+        side stream                  all_gather(k)  ------------------^ (event)
+
+    `step()` enqueues one step of this rank's shard (cmb200_put_step: asynchronous, the 32-byte
+    exchange records are packed on the device), starts ONE all-gather of those records (NCCL over
+    NVLink) on a side stream, and imports the previous step's gathered records into the index replica
+    (cmb200_import_records_dev, one claim + one apply launch).  The all-gather of step k therefore
+    overlaps the encode of step k+1; nothing in the sequence waits on the host.  Importing a step's
+    records after the next local put is harmless: last-writer-wins is decided by the global stream
+    position each record carries, not by arrival order (SURVEY.md App. B rule 4).  With one rank
+    there is no exchange and `step()` is cmb200_put_step alone.  Call `flush()` after the last step.
+    """
+
+    def __init__(self, engine, n_per_step: int, rank: int, world: int, device, timing: bool = False):
+        import torch
+        self.torch = torch
+        self.eng, self.n, self.rank, self.world = engine, n_per_step, rank, world
+        self.dev = torch.device(device)
+        self.main = torch.cuda.ExternalStream(engine.stream(), device=self.dev)
+        self.rec = [torch.empty((n_per_step, REC_WORDS), dtype=torch.int64, device=self.dev) for _ in range(2)]
+        self.count = 0
+        self.pending = None
+        self.timing = timing
+        self.times = {"allgather": [], "import": []}      # lists of (start, end) event pairs
+        if world > 1:
+            self.side = torch.cuda.Stream(device=self.dev)
+            self.gath = [torch.empty((world * n_per_step, REC_WORDS), dtype=torch.int64, device=self.dev) for _ in range(2)]
+            self.put_done = [torch.cuda.Event() for _ in range(2)]
+            self.gathered = [torch.cuda.Event() for _ in range(2)]
+        torch.cuda.synchronize(self.dev)
+
+    def _timed(self, stream):
+        if not self.timing:
+            return None
+        e = self.torch.cuda.Event(enable_timing=True)
+        e.record(stream)
+        return e
+
+    def _import(self, k: int):
+        self.main.wait_event(self.gathered[k])
+        a = self._timed(self.main)
+        self.eng.import_records_dev(self.world * self.n, self.gath[k].data_ptr(), self.rank)
+        b = self._timed(self.main)
+        if a is not None:
+            self.times["import"].append((a, b))
+
+    def step(self, u, l, pages, on_dev, ts=None, lens=None, next_seq=None) -> int:
+        """One step: chunk i of this rank is global stream position next_seq + world * i
+        (set_stream_order is applied when next_seq is given).  -> ticket for engine.wait()."""
+        import torch.distributed as dist
+        torch = self.torch
+        k = self.count & 1
+        self.count += 1
+        if next_seq is not None:
+            self.eng.set_stream_order(int(next_seq), self.world)
+        with torch.cuda.stream(self.main):
+            ticket = self.eng.put_step(u, l, pages, ts=ts, on_dev=on_dev, rank=self.rank,
+                                       records_dev=self.rec[k].data_ptr(), lens=lens)
+        if self.world > 1:
+            self.put_done[k].record(self.main)
+            self.side.wait_event(self.put_done[k])
+            with torch.cuda.stream(self.side):
+                a = self._timed(self.side)
+                dist.all_gather_into_tensor(self.gath[k], self.rec[k])
+                b = self._timed(self.side)
+            if a is not None:
+                self.times["allgather"].append((a, b))
+            self.gathered[k].record(self.side)
+            if self.pending is not None:
+                self._import(self.pending)
+            self.pending = k
+        return ticket
+
+    def flush(self):
+        """Imports the last step's records (enqueued on the engine's stream; not a host sync)."""
+        if self.world > 1 and self.pending is not None:
+            self._import(self.pending)
+            self.pending = None
+
+    def last_lens(self) -> np.ndarray:
+        """Stored block lengths of the most recent step (-1 = stored nothing), from its records."""
+        k = (self.count - 1) & 1
+        self.torch.cuda.synchronize(self.dev)
+        tail = self.rec[k][:, 3].cpu().numpy()
+        return (((tail & 0xFFFFFFFF) ^ 0x80000000) - 0x80000000).astype(np.int64)
+
+    def breakdown_ms(self) -> dict:
+        """Mean device time of the exchange stages (needs timing=True and a synchronized device)."""
+        out = {}
+        for key, pairs in self.times.items():
+            if pairs:
+                out[key + "_ms"] = float(np.mean([a.elapsed_time(b) for a, b in pairs]))
+        return out

@@ -58,6 +58,13 @@ def lib() -> C.CDLL:
         L.ef_cpu_bench_store.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                          C.c_int, C.c_void_p]
+        L.ef_gen_chunk.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p]
+        L.ef_gen_chunks.argtypes = [C.c_uint64, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p, C.c_int]
+        L.ef_gen_addr.argtypes = [C.c_uint64, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p]
+        L.ef_gen_stream_ids.restype = C.c_uint64
+        L.ef_gen_stream_ids.argtypes = [C.c_uint64, C.c_size_t, C.c_double, C.c_uint64, C.c_void_p]
+        L.ef_parity_records.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p,
+                                        C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         _LIB = L
     return _LIB
 
@@ -87,6 +94,55 @@ def ref():
             R.filemap_entries.argtypes = [C.c_void_p]
             _REF = R
     return _REF
+
+
+def gen_chunks(seed: int, cids, bsize: int = 65536, threads: int = 0, out: np.ndarray | None = None) -> np.ndarray:
+    """[n, bsize] uint8 pages of the synthetic stream (oracle/streamgen.c), `threads` pthreads."""
+    cids = np.ascontiguousarray(cids, dtype=np.uint64)
+    if out is None:
+        out = np.empty((len(cids), bsize), dtype=np.uint8)
+    assert out.flags.c_contiguous and out.size == len(cids) * bsize
+    lib().ef_gen_chunks(seed, cids.ctypes.data, len(cids), bsize, out.ctypes.data, threads or (os.cpu_count() or 1))
+    return out
+
+
+def gen_addr(seed: int, cids, pshift: int = 16):
+    """-> (offset, nhid_small) arrays of the stream's addresses."""
+    cids = np.ascontiguousarray(cids, dtype=np.uint64)
+    off = np.empty(len(cids), dtype=np.uint64)
+    nh = np.empty(len(cids), dtype=np.uint64)
+    lib().ef_gen_addr(seed, cids.ctypes.data, len(cids), pshift, off.ctypes.data, nh.ctypes.data)
+    return off, nh
+
+
+def gen_stream_ids(n: int, dup: float, seed2: int = 43, first_cid: int = 0):
+    """-> (cids, distinct): stream with a fraction `dup` of same-address repeats."""
+    cids = np.empty(n, dtype=np.uint64)
+    distinct = lib().ef_gen_stream_ids(seed2, n, float(dup), first_cid, cids.ctypes.data)
+    return cids, int(distinct)
+
+
+def parity_records(pages: np.ndarray, u, l, recs: np.ndarray, rec_lens, put_lens=None, accel: int = 12,
+                   threads: int = 0) -> dict:
+    """The parity gate of a measured run: every stored record must be the 24-byte prefix + the LZ4
+    block that the reference's LZ4_compress_fast (oracle/_ref; the port when it is absent) makes of
+    the page.  recs = [n, stride] uint8 as read back from the GPU store."""
+    R = ref()
+    enc = C.cast(R.LZ4_compress_fast, C.c_void_p) if R is not None else C.cast(lib().ef_port_compress_fast, C.c_void_p)
+    pages = np.ascontiguousarray(pages, dtype=np.uint8)
+    n, bsize = pages.shape
+    addr = np.empty((n, 2), dtype=np.uint64)
+    addr[:, 0], addr[:, 1] = u, l
+    rec_lens = np.ascontiguousarray(rec_lens, dtype=np.int32)
+    pl = None if put_lens is None else np.ascontiguousarray(put_lens, dtype=np.int32)
+    recs = np.ascontiguousarray(recs, dtype=np.uint8)
+    out = (C.c_double * 3)()
+    lib().ef_parity_records(enc, pages.ctypes.data, n, bsize, accel, addr.ctypes.data, recs.ctypes.data,
+                            recs.strides[0], rec_lens.ctypes.data, pl.ctypes.data if pl is not None else None,
+                            threads or (os.cpu_count() or 1), out)
+    return {"chunks": int(n), "mismatches": int(out[0]), "first_mismatch": int(out[1]),
+            "against": "oracle/_ref (reference LZ4_compress_fast + data_prefix)" if R is not None else "oracle port",
+            "block_bytes": int(out[2])}
 
 
 def _u8(a) -> np.ndarray:

@@ -123,3 +123,46 @@ def test_fingerprint_self_consistency(oracle):
     assert f(z1) != f(z2)
     seen = {f(datagen.make_page("Z", 4096, s)) for s in range(200)}
     assert len(seen) == len({bytes(datagen.make_page("Z", 4096, s)) for s in range(200)})
+
+
+def test_stream_generators_agree(oracle, E):
+    """oracle/streamgen.c and the product's generator (csrc/streamgen.cuh, host form) are two
+    independent statements of the benchmark stream: same pages, addresses and duplicate pattern."""
+    import numpy as np
+    cids = np.concatenate([np.arange(0, 24, dtype=np.uint64), np.array([16383, 16384, 70001, 2**33 + 5], dtype=np.uint64)])
+    for bsize in (4096, 65536, 131072):
+        pages = oracle.gen_chunks(42, cids, bsize, threads=3)
+        for i, c in enumerate(cids):
+            assert (pages[i] == E.gen_chunk_host(42, int(c), bsize)).all(), (bsize, int(c))
+    off_o, nh_o = oracle.gen_addr(42, cids, 16)
+    off_p, nh_p = E.gen_addr(42, cids, 16)
+    assert (off_o == off_p).all() and (nh_o == nh_p).all()
+    for dup in (0.0, 0.3, 0.5):
+        a, da = oracle.gen_stream_ids(5000, dup)
+        b, db = E.gen_stream_ids(5000, dup)
+        assert da == db and (a == b).all()
+
+
+def test_parity_gate_detects_a_wrong_record(oracle):
+    """The bench's parity gate (oracle.parity_records) accepts the reference's records and flags a
+    single flipped byte, a wrong length and a wrong prefix."""
+    import numpy as np
+    cids = np.arange(12, dtype=np.uint64)
+    pages = oracle.gen_chunks(42, cids, 65536, threads=2)
+    u = np.arange(12, dtype=np.uint64) + 7
+    l = np.arange(12, dtype=np.uint64)
+    recs = np.zeros((12, 24 + 65536 + 1024), dtype=np.uint8)
+    lens = np.zeros(12, dtype=np.int32)
+    for i in range(12):
+        blk = oracle.ref_lz4_encode(pages[i]) if oracle.ref() is not None else oracle.lz4_encode(pages[i])
+        rec = oracle.record_prefix(int(u[i]), int(l[i]), len(blk)) + blk
+        recs[i, :len(rec)] = np.frombuffer(rec, dtype=np.uint8)
+        lens[i] = len(rec)
+    ok = oracle.parity_records(pages, u, l, recs, lens, lens - 24, threads=3)
+    assert ok["mismatches"] == 0 and ok["chunks"] == 12
+    bad = recs.copy(); bad[5, 100] ^= 1
+    assert oracle.parity_records(pages, u, l, bad, lens, threads=3)["mismatches"] == 1
+    assert oracle.parity_records(pages, u, l, bad, lens, threads=3)["first_mismatch"] == 5
+    l2 = lens.copy(); l2[0] -= 1
+    assert oracle.parity_records(pages, u, l, recs, l2, threads=1)["mismatches"] == 1
+    assert oracle.parity_records(pages, u + np.uint64(1), l, recs, lens, threads=2)["mismatches"] == 12
