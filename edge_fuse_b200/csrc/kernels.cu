@@ -338,19 +338,24 @@ __device__ uint32_t commit_direct(const EncodeJob &job, uint32_t i, uint32_t idx
 	return reuse ? 0u : need;
 }
 
-// ENC 0: page read through the L1 (lz4_encode.cuh).  ENC 1: parse frontier staged in a per-warp
+// ENC 0: lean loop, page read through the L1.  ENC 1: lean loop, parse frontier staged in a per-warp
 // shared-memory ring by TMA (lz4_encode_ring.cuh); shared memory = tables | rings | mbarriers.
+// ENC 2: the round-1 loop (lz4_encode.cuh), kept for comparison.
 // FPNA: the fingerprint's streaming loads do not allocate in the L1.
+// Launch bounds = the real launch shapes (2 CTAs x 7 warps, or 1 CTA x 13 warps with the ring), so
+// that the register allocator may use what the SM has (146 / 157 registers per thread) instead of
+// rematerialising loop invariants inside the parse loop.
+constexpr int ENC_PLAIN_WARPS = 7, ENC_RING_WARPS = 13;
 template <bool WIDE, int ENC, bool FPNA>
-__global__ void __launch_bounds__(512, 1) k_encode(EncodeJob job) {
+__global__ void __launch_bounds__(ENC == 1 ? ENC_RING_WARPS * 32 : ENC_PLAIN_WARPS * 32, ENC == 1 ? 1 : 2) k_encode(EncodeJob job) {
 	extern __shared__ __align__(128) uint8_t smem[];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const uint32_t nwarps = blockDim.x >> 5;
 	uint8_t *wsm = smem + (size_t)warp * LZ4_TABLE_BYTES;
 	PageRing ring;
 	if (ENC == 1)
-		ring_setup(ring, smem + (size_t)nwarps * LZ4_TABLE_BYTES + (size_t)warp * RING_BYTES,
-		    smem + (size_t)nwarps * (LZ4_TABLE_BYTES + RING_BYTES) + (size_t)warp * RING_MBAR_BYTES, lane);
+		ring_setup(ring, smem + (size_t)nwarps * LZ4_TABLE_BYTES + (size_t)warp * RING_ALLOC,
+		    smem + (size_t)nwarps * (LZ4_TABLE_BYTES + RING_ALLOC) + (size_t)warp * RING_MBAR_BYTES, lane);
 	const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + warp;         // resident warp slot
 	const bool direct = job.slot_idx != nullptr && job.arena.seg_bytes != 0u && job.accel != 0u && gw < ARENA_SEG_SLOTS;
 	// room one chunk may need while it is being encoded: prefix + a stage row (filemap.c:120 dest[bsize+1024])
@@ -404,12 +409,12 @@ __global__ void __launch_bounds__(512, 1) k_encode(EncodeJob job) {
 		}
 		uint32_t clen;
 		if (job.fps) {                  // fingerprint along the parse frontier: the page is read once
-			if (ENC == 1) clen = lz4_encode_ring<WIDE, true, FPNA>(src, job.nbytes, dst, job.accel, wsm, ring, lane, fp_hi, fp_lo);
-			else clen = lz4_encode_warp<WIDE, true, FPNA>(src, job.nbytes, dst, job.accel, wsm, lane, fp_hi, fp_lo);
+			if (ENC == 2) clen = lz4_encode_warp<WIDE, true, FPNA>(src, job.nbytes, dst, job.accel, wsm, lane, fp_hi, fp_lo);
+			else clen = lz4_encode_lean<WIDE, true, FPNA, ENC == 1>(src, job.nbytes, dst, job.accel, wsm, ring, lane, fp_hi, fp_lo);
 			if (lane == 0) { job.fps[2 * (size_t)i] = fp_hi; job.fps[2 * (size_t)i + 1] = fp_lo; }
 		} else {
-			if (ENC == 1) clen = lz4_encode_ring<WIDE, false, false>(src, job.nbytes, dst, job.accel, wsm, ring, lane, fp_hi, fp_lo);
-			else clen = lz4_encode_warp<WIDE, false, false>(src, job.nbytes, dst, job.accel, wsm, lane, fp_hi, fp_lo);
+			if (ENC == 2) clen = lz4_encode_warp<WIDE, false, false>(src, job.nbytes, dst, job.accel, wsm, lane, fp_hi, fp_lo);
+			else clen = lz4_encode_lean<WIDE, false, false, ENC == 1>(src, job.nbytes, dst, job.accel, wsm, ring, lane, fp_hi, fp_lo);
 		}
 		if (lane == 0) job.lens[i] = (int32_t)clen;
 		if (store) {
@@ -675,21 +680,22 @@ static int launch_encode_kernel(K kern, const EncodeJob &job, int warps, int cta
 
 // Plain organisation: residency is bounded by shared memory, one 16 KiB position table per chunk,
 // 14 of them in the 227 KiB of an SM (2 CTAs x 7 warps); chunks handed out dynamically.
+template <int ENC>
 static int launch_encode_warps(const EncodeJob &job, cudaStream_t st, bool fpna) {
-	static int warps = env_int("CMB200_ENC_WARPS", 7, 1, 14);
-	static int ctas = env_int("CMB200_ENC_CTAS_PER_SM", 2, 1, 8);
+	static int warps = env_int("CMB200_ENC_WARPS", ENC_PLAIN_WARPS, 1, ENC_PLAIN_WARPS);
+	static int ctas = env_int("CMB200_ENC_CTAS_PER_SM", 2, 1, 2);
 	const size_t smem = (size_t)warps * LZ4_TABLE_BYTES;
 	const bool wide = job.nbytes >= LZ4_NARROW_LIMIT;
-	if (wide) return fpna ? launch_encode_kernel(k_encode<true, 0, true>, job, warps, ctas, smem, st)
-	                      : launch_encode_kernel(k_encode<true, 0, false>, job, warps, ctas, smem, st);
-	return fpna ? launch_encode_kernel(k_encode<false, 0, true>, job, warps, ctas, smem, st)
-	            : launch_encode_kernel(k_encode<false, 0, false>, job, warps, ctas, smem, st);
+	if (wide) return fpna ? launch_encode_kernel(k_encode<true, ENC, true>, job, warps, ctas, smem, st)
+	                      : launch_encode_kernel(k_encode<true, ENC, false>, job, warps, ctas, smem, st);
+	return fpna ? launch_encode_kernel(k_encode<false, ENC, true>, job, warps, ctas, smem, st)
+	            : launch_encode_kernel(k_encode<false, ENC, false>, job, warps, ctas, smem, st);
 }
 
 // Ring organisation (lz4_encode_ring.cuh): table + 1 KiB TMA ring + mbarriers per warp, 13 chunks
 // per SM in one CTA.
 static int launch_encode_ring(const EncodeJob &job, cudaStream_t st, bool fpna) {
-	static int warps = env_int("CMB200_RING_WARPS", 13, 1, 13);
+	static int warps = env_int("CMB200_RING_WARPS", ENC_RING_WARPS, 1, ENC_RING_WARPS);
 	const size_t smem = (size_t)warps * RING_WARP_SMEM;
 	const bool wide = job.nbytes >= LZ4_NARROW_LIMIT;
 	if (wide) return fpna ? launch_encode_kernel(k_encode<true, 1, true>, job, warps, 1, smem, st)
@@ -710,9 +716,9 @@ int launch_encode(const EncodeJob &job_in, cudaStream_t st) {
 	//               pages in 16 Ki-chunk launches, slower on incompressible ones and small launches.
 	// Running both at once on one batch (shared chunk counter, two streams) was measured too: the
 	// SM does not add the two up (profiles/r1_encode_notes.md).
-	static int mode = env_int("CMB200_ENC_MODE", 0, 0, 2);
+	static int mode = env_int("CMB200_ENC_MODE", 2, 0, 3);
 	static int grp_ctas = env_int("CMB200_GRP_CTAS_PER_SM", 6, 1, 6);
-	static int fpna = env_int("CMB200_FP_NOALLOC", 0, 0, 1);
+	static int fpna = env_int("CMB200_FP_NOALLOC", 1, 0, 1);
 	EncodeJob job = job_in;
 	if (mode == 1) {
 		// the fingerprint is fused into the warp kernel; the group kernel takes it from a pass before
@@ -724,7 +730,8 @@ int launch_encode(const EncodeJob &job_in, cudaStream_t st) {
 	const bool ring_ok = job.accel >= 1 && job.accel <= RING_MAX_ACCEL && job.nbytes < (1u << 24) &&
 	    (reinterpret_cast<uintptr_t>(job.pages) & 15u) == 0 && (job.page_stride & 15u) == 0;
 	if (mode == 2 && ring_ok) return launch_encode_ring(job, st, fpna != 0);
-	return launch_encode_warps(job, st, fpna != 0);
+	if (mode == 3) return launch_encode_warps<2>(job, st, fpna != 0);      // the round-1 loop
+	return launch_encode_warps<0>(job, st, fpna != 0);
 }
 
 // ------------------------------------------------------------------------------------------

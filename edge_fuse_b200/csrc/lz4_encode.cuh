@@ -125,7 +125,14 @@ __device__ __noinline__ void lz4_copy_literals(uint8_t *dst, const uint8_t *src,
 // 512 bytes per step for the long matches of repetitive pages.
 __device__ __noinline__ uint32_t lz4_count_long(const uint8_t *src, uint32_t a, uint32_t b, uint32_t lim,
     uint32_t lim4, int lane) {
-	uint32_t total = 0;
+	// most matches that outgrow the neighbourhoods end within the next few bytes: one byte per lane first
+	{
+		const uint32_t pa = a + (uint32_t)lane;
+		const bool same = pa < lim && ldg8(src + pa) == ldg8(src + b + (uint32_t)lane);
+		const uint32_t stop = __ballot_sync(CMB_FULL, !same);
+		if (stop) return (uint32_t)(__ffs(stop) - 1);
+	}
+	uint32_t total = 32;
 	for (;;) {
 		const uint32_t pa = a + total + 16u * lane;
 		uint32_t nb = 0;                                  // equal bytes in this lane's 16
@@ -221,7 +228,11 @@ __device__ __noinline__ uint32_t lz4_emit_general(uint8_t *dst, uint32_t op, con
 	if (lane == 0) dst[op] = (uint8_t)((min(lit, 15u) << 4) | min(mc, 15u));
 	op++;
 	if (lit >= 15u) op = lz4_emit_len(dst, op, lit - 15u, lane);
-	warp_copy_ro(dst + op, src + anchor, lit, lane);
+	if (lit <= 256u) {           // the usual case here is a run of 65..200 bytes: bytes, no alignment work
+		for (uint32_t i = lane; i < lit; i += 32) dst[op + i] = (uint8_t)ldg8(src + anchor + i);
+	} else {
+		warp_copy_ro(dst + op, src + anchor, lit, lane);
+	}
 	op += lit;
 	if (lane == 0) { dst[op] = (uint8_t)off; dst[op + 1] = (uint8_t)(off >> 8); }
 	op += 2;

@@ -32,10 +32,12 @@
 namespace cmb {
 
 constexpr uint32_t RING_BYTES = 1024, RING_BUF = 256, RING_BUFS = 4;
+constexpr uint32_t RING_MIRROR = 16;       // the ring's first 16 bytes again behind its end: a 16-byte read never wraps
+constexpr uint32_t RING_ALLOC = RING_BYTES + 64;   // per-warp allocation (ring + mirror, keeps 64-byte alignment)
 constexpr uint32_t RING_AHEAD = 376;      // a batch reads page bytes [anchor - 4, anchor + RING_AHEAD)
 constexpr uint32_t RING_MAX_ACCEL = 12;   // 2 + accel * 29 + 12 <= RING_AHEAD, first batch 2 + accel * 30 + 12
 constexpr uint32_t RING_MBAR_BYTES = 64;  // 4 x 8-byte mbarriers, padded
-constexpr uint32_t RING_WARP_SMEM = LZ4_TABLE_BYTES + RING_BYTES + RING_MBAR_BYTES;
+constexpr uint32_t RING_WARP_SMEM = LZ4_TABLE_BYTES + RING_ALLOC + RING_MBAR_BYTES;
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t arrivals) {
@@ -93,17 +95,17 @@ __device__ __forceinline__ void ring_setup(PageRing &ring, uint8_t *ring_smem, u
 	__syncwarp();
 }
 
-__device__ __forceinline__ bool ring_needs_advance(const PageRing &ring, uint32_t g_lo, uint32_t g_hi, uint32_t nbufs) {
-	return g_hi >= ring.ready || (ring.issued < nbufs && ring.issued < g_lo + RING_BUFS);
-}
-
-// Makes page buffers [g_lo, g_hi] resident (g_hi - g_lo <= 2) and requests the ones that follow,
-// up to the ring's capacity.  Every buffer that was requested is waited for exactly once and in
-// order, so a ring buffer is never handed to TMA again while an earlier copy into it is in flight.
+// Called when the parse frontier enters page buffer g_lo (and once at the start of a page): makes
+// buffers [g_lo, g_lo + 2] resident — a batch reads bytes [anchor - 4, anchor + RING_AHEAD), which
+// never reach past g_lo + 2 — and requests g_lo + 3.  In the steady state that is one wait (for
+// the buffer requested two crossings ago) and one request.  Every buffer that was requested is
+// waited for exactly once and in order, also those a long match jumped over, so a ring buffer is
+// never handed to TMA again while an earlier copy into it is in flight.
 // state = issued | ready << 16 | parity << 32, in and out (page sizes up to 2^20: < 2^16 buffers).
 __device__ __noinline__ uint64_t ring_advance(uint32_t s_bytes, uint32_t s_bar, uint64_t state, const uint8_t *src,
-    uint32_t n, uint32_t nbufs, uint32_t g_lo, uint32_t g_hi, int lane) {
+    uint32_t n, uint32_t nbufs, uint32_t g_lo, int lane) {
 	uint32_t issued = (uint32_t)state & 0xffffu, ready = (uint32_t)(state >> 16) & 0xffffu, parity = (uint32_t)(state >> 32);
+	const uint32_t g_hi = min(g_lo + 2u, nbufs - 1u);
 	// (1) requested buffers that are needed, or that the parse has already left behind (a long match
 	//     jumped over them), must have landed before their ring buffer can be reused
 	const uint32_t upto = min(issued, g_hi + 1u);
@@ -113,26 +115,27 @@ __device__ __noinline__ uint64_t ring_advance(uint32_t s_bytes, uint32_t s_bar, 
 	// (3) request what the ring has room for: buffers below g_lo are dead, so [g_lo, g_lo + 4) fit
 	const uint32_t want = min(g_lo + RING_BUFS, nbufs);
 	__syncwarp();                                   // every lane is done reading the buffers being replaced
-	if (lane == 0 && issued < want) {
-		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy reads before async-proxy writes
+	if (lane == 0) {
 		for (uint32_t g = issued; g < want; g++) {
 			const uint32_t r = g & (RING_BUFS - 1u);
 			// whole 16-byte units; the last buffer of a ragged page reads < 16 bytes past its end
 			// (page buffers are padded, lz4_encode_warp's contract)
 			const uint32_t nb = min(RING_BUF, (n - g * RING_BUF + 15u) & ~15u);
-			mbar_expect_tx(s_bar + 8u * r, nb);
-			tma_load_1d(s_bytes + r * RING_BUF, src + (size_t)g * RING_BUF, nb, s_bar + 8u * r);
+			const uint8_t *from = src + (size_t)g * RING_BUF;
+			mbar_expect_tx(s_bar + 8u * r, nb + (r == 0u ? RING_MIRROR : 0u));
+			tma_load_1d(s_bytes + r * RING_BUF, from, nb, s_bar + 8u * r);
+			if (r == 0u) tma_load_1d(s_bytes + RING_BYTES, from, RING_MIRROR, s_bar);   // the mirror of the ring's head
 		}
 	}
 	if (issued < want) issued = want;
-	// (4) what this batch reads
+	// (4) what the batches in this buffer read
 	while (ready <= g_hi) { ring_wait_buf(s_bar, parity, ready); ready++; }
 	return (uint64_t)issued | ((uint64_t)ready << 16) | ((uint64_t)parity << 32);
 }
 __device__ __forceinline__ void ring_step(PageRing &ring, const uint8_t *src, uint32_t n, uint32_t nbufs, uint32_t g_lo,
-    uint32_t g_hi, int lane) {
+    int lane) {
 	const uint64_t st = ring_advance(ring.s_bytes, ring.s_bar,
-	    (uint64_t)ring.issued | ((uint64_t)ring.ready << 16) | ((uint64_t)ring.parity << 32), src, n, nbufs, g_lo, g_hi, lane);
+	    (uint64_t)ring.issued | ((uint64_t)ring.ready << 16) | ((uint64_t)ring.parity << 32), src, n, nbufs, g_lo, lane);
 	ring.issued = (uint32_t)st & 0xffffu; ring.ready = (uint32_t)(st >> 16) & 0xffffu; ring.parity = (uint32_t)(st >> 32);
 }
 // nothing may be in flight when the page (or the kernel) ends
@@ -140,14 +143,12 @@ __device__ __forceinline__ void ring_drain(PageRing &ring) {
 	while (ring.ready < ring.issued) { ring_wait_buf(ring.s_bar, ring.parity, ring.ready); ring.ready++; }
 }
 
-// The 12 page bytes [p-4, p+8) from the ring (p inside the resident window), as lz4_around.
+// The 12 page bytes [p-4, p+8) from the ring (p inside the resident window), as lz4_around: one
+// address, four shared-memory words at fixed offsets (the mirrored tail absorbs the wrap).
 __device__ __forceinline__ Lz4Around ring_around(const uint8_t *ring, uint32_t p) {
-	const uint32_t a = p & ~3u, sh = (p & 3u) * 8u;
-	const uint32_t b = a - ((a != 0u) ? 4u : 0u);        // p < 4: the word before the page is never needed
-	const uint32_t w0 = *reinterpret_cast<const uint32_t *>(ring + (b & (RING_BYTES - 1u)));
-	const uint32_t w1 = *reinterpret_cast<const uint32_t *>(ring + (a & (RING_BYTES - 1u)));
-	const uint32_t w2 = *reinterpret_cast<const uint32_t *>(ring + ((a + 4u) & (RING_BYTES - 1u)));
-	const uint32_t w3 = *reinterpret_cast<const uint32_t *>(ring + ((a + 8u) & (RING_BYTES - 1u)));
+	const uint32_t sh = (p & 3u) * 8u;
+	const uint32_t *q = reinterpret_cast<const uint32_t *>(ring + (((p & ~3u) - 4u) & (RING_BYTES - 1u)));
+	const uint32_t w0 = q[0], w1 = q[1], w2 = q[2], w3 = q[3];     // p < 4: w0 is not page data, and is never used
 	Lz4Around r;
 	r.before = __funnelshift_r(w0, w1, sh);
 	r.at = __funnelshift_r(w1, w2, sh);
@@ -156,13 +157,19 @@ __device__ __forceinline__ Lz4Around ring_around(const uint8_t *ring, uint32_t p
 }
 
 // Encodes src[0,n) into dst; returns the block length (uniform across the warp).  Same contract as
-// lz4_encode_warp, plus: accel <= RING_MAX_ACCEL, src 16-byte aligned, `ring` set up by this warp.
+// lz4_encode_warp.  RING: the probe neighbourhoods and literal bytes come from the warp's TMA ring
+// (accel <= RING_MAX_ACCEL, src 16-byte aligned, `ring` set up by this warp); otherwise from global
+// memory through the L1.
 // One lane layout for every batch: lane 0 refills the slot of end-2 (lz4.c:691), lane 1 re-tests
 // `end` (lz4.c:694-707), lane j >= 2 is probe j-2 of the search that starts at end+1
 // (lz4.c:593-619).  The first search of a page (lz4.c:583-584: from position 1, nothing before it)
 // is the same batch with end = 0 and the two special lanes switched off.
-template <bool WIDE, bool FP, bool FP_NOALLOC>
-__device__ uint32_t lz4_encode_ring(const uint8_t *__restrict__ src, uint32_t n, uint8_t *__restrict__ dst,
+// The loop is written for a short in-order instruction stream (a warp issues in order; with one
+// chain per warp every instruction of the body costs issue time whether or not the next sequence
+// depends on it): everything that changes only every few hundred bytes — the fingerprint frontier,
+// the ring — hangs off ONE comparison of the anchor with the position of the next such event.
+template <bool WIDE, bool FP, bool FP_NOALLOC, bool RING>
+__device__ uint32_t lz4_encode_lean(const uint8_t *__restrict__ src, uint32_t n, uint8_t *__restrict__ dst,
     uint32_t accel, uint8_t *tab_smem, PageRing &ring, int lane, uint64_t &fp_hi, uint64_t &fp_lo) {
 	Lz4Table<WIDE> tab;
 	tab.t = reinterpret_cast<decltype(tab.t)>(tab_smem);
@@ -185,27 +192,68 @@ __device__ uint32_t lz4_encode_ring(const uint8_t *__restrict__ src, uint32_t n,
 		const uint32_t mlimit = n - LZ4_TAIL_LITERALS;
 		const uint32_t nbufs = (n + RING_BUF - 1u) / RING_BUF;
 		const uint8_t *const rb = ring.bytes;
-		ring.issued = ring.ready = 0;
+		if (RING) ring.issued = ring.ready = 0;
 		const bool special = lane < 2;
 		const uint32_t kk = (uint32_t)lane - 2u;
-		const uint32_t delta2 = special ? 2u * (uint32_t)lane - 2u : 1u + (kk ? 1u + accel * (kk - 1u) : 0u);
-		const uint32_t need2 = special ? 0u : 2u + accel * kk;             // enabled while end + need2 <= mflimit
+		uint32_t delta2 = special ? 2u * (uint32_t)lane - 2u : 1u + (kk ? 1u + accel * (kk - 1u) : 0u);
+		// A lane takes part while anchor < en_below: the probe after its own must stay <= mflimit
+		// (lz4.c:601), i.e. anchor + need2 <= mflimit; the special lanes take part once a match has
+		// ended (0 until then, everything afterwards).
+		const uint32_t need2 = 2u + accel * kk;
+		uint32_t en_below = special ? 0u : (mflimit >= need2 ? mflimit - need2 + 1u : 0u);
+		const uint32_t special_on = special ? 0xffffffffu : 0u;
+		// the two per-lane values the loop uses stay in registers (the compiler otherwise recomputes
+		// them from the lane number on the critical path of every iteration)
+		asm volatile("" : "+r"(delta2), "+r"(en_below));
 		bool started = false;                                              // a match has ended (uniform)
+		uint32_t next_event = 0;                                           // anchor at which the frontiers move next
 		for (;;) {
-			if (FP) fp.upto(src, anchor + 512u, lane);
-			{
-				const uint32_t g_lo = (max(anchor, 4u) - 4u) / RING_BUF;
-				const uint32_t g_hi = min((anchor + RING_AHEAD - 1u) / RING_BUF, nbufs - 1u);
-				if (ring_needs_advance(ring, g_lo, g_hi, nbufs)) ring_step(ring, src, n, nbufs, g_lo, g_hi, lane);
+			if (anchor >= next_event) {
+				// every 256 bytes: ring buffers, then fingerprint stripes up to the probes (in this order:
+				// the ring's out-of-line path would otherwise wait for the stripe the fingerprint prefetches)
+				if (RING) {
+					const uint32_t g_lo = (max(anchor, 4u) - 4u) / RING_BUF;
+					if (ring.ready == g_lo + 2u && ring.issued == g_lo + 3u && g_lo + 3u < nbufs) {
+						// steady state: the frontier moved on by one buffer.  Request g_lo + 3 into the buffer
+						// g_lo - 1 has just left, wait for g_lo + 2 (requested two buffers ago).
+						__syncwarp();
+						if (lane == 0) {
+							const uint32_t g = g_lo + 3u, r = g & (RING_BUFS - 1u);
+							const uint32_t nb = min(RING_BUF, (n - g * RING_BUF + 15u) & ~15u);
+							const uint8_t *from = src + (size_t)g * RING_BUF;
+							mbar_expect_tx(ring.s_bar + 8u * r, nb + (r == 0u ? RING_MIRROR : 0u));
+							tma_load_1d(ring.s_bytes + r * RING_BUF, from, nb, ring.s_bar + 8u * r);
+							if (r == 0u) tma_load_1d(ring.s_bytes + RING_BYTES, from, RING_MIRROR, ring.s_bar);
+						}
+						ring.issued = g_lo + 4u;
+						ring_wait_buf(ring.s_bar, ring.parity, g_lo + 2u);
+						ring.ready = g_lo + 3u;
+					} else {
+						ring_step(ring, src, n, nbufs, g_lo, lane);
+					}
+					next_event = (g_lo + 1u) * RING_BUF + 4u;
+				} else {
+					next_event = (anchor | 255u) + 1u;
+				}
+				if (FP) fp.upto(src, anchor + 512u, lane);
 			}
-			const bool en = special ? started : (anchor + need2 <= mflimit);
-			const uint32_t pos = en ? anchor + delta2 : 0u;        // disabled lanes read (and ignore) whatever sits at ring offset 0
-			// speculative literal bytes: src[anchor + lane], src[anchor + 32 + lane] (used when the run is <= 64 bytes)
-			const uint32_t litbyte = rb[min(anchor + (uint32_t)lane, n - 1u) & (RING_BYTES - 1u)];
-			const uint32_t litbyte2 = rb[min(anchor + 32u + (uint32_t)lane, n - 1u) & (RING_BYTES - 1u)];
+			const bool en = anchor < en_below;
+			const uint32_t pos = en ? anchor + delta2 : 0u;        // disabled lanes read (and ignore) position 0 / ring offset 0
+			// speculative literal bytes: src[anchor + lane], src[anchor + 32 + lane] (used when the run is <= 64 bytes;
+			// never stored beyond the literal run, so reading past the page end is harmless in the ring)
+			uint32_t litbyte, litbyte2;
+			Lz4Around ai;
+			if (RING) {
+				litbyte = rb[(anchor + (uint32_t)lane) & (RING_BYTES - 1u)];
+				litbyte2 = rb[(anchor + 32u + (uint32_t)lane) & (RING_BYTES - 1u)];
+				ai = ring_around(rb, pos);
+			} else {
+				litbyte = ldg8(src + min(anchor + (uint32_t)lane, n - 1u));
+				litbyte2 = ldg8(src + min(anchor + 32u + (uint32_t)lane, n - 1u));
+				ai = lz4_around<CMB_LZ4_HINT_PROBE>(src, pos);
+			}
 
 			// ---- unified batch ----
-			const Lz4Around ai = ring_around(rb, pos);
 			const uint32_t pseq = ai.at;
 			const uint32_t h = WIDE ? lz4_hash5((uint64_t)ai.at | ((uint64_t)ai.next << 32)) : lz4_hash4(ai.at);
 			const uint32_t cand = tab.get(h);
@@ -216,7 +264,8 @@ __device__ uint32_t lz4_encode_ring(const uint8_t *__restrict__ src, uint32_t n,
 			const uint32_t seen = tab.get(h);
 			__syncwarp();                                           // read-backs done before any undo store
 			const bool foreign = en && seen != (WIDE ? pos : (pos & 0xffffu));
-			const bool hit = en && lane != 0 && cand + LZ4_FAR >= pos && ac.at == pseq;
+			bool hit = en && lane != 0 && ac.at == pseq;
+			if (WIDE) hit = hit && cand + LZ4_FAR >= pos;           // byU16: every distance fits (lz4.c:617)
 			const uint32_t foreigns = __ballot_sync(CMB_FULL, foreign);
 			const uint32_t hits = __ballot_sync(CMB_FULL, hit);
 			uint32_t nf, nb;
@@ -289,9 +338,10 @@ __device__ uint32_t lz4_encode_ring(const uint8_t *__restrict__ src, uint32_t n,
 
 			anchor = end;
 			started = true;
+			en_below |= special_on;
 			if (end > mflimit) break;                     // lz4.c:688
 		}
-		ring_drain(ring);
+		if (RING) ring_drain(ring);
 	}
 
 	// ---- last literals (lz4.c:713-729) ----

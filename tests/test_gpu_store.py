@@ -693,3 +693,110 @@ def test_snapshot_format_against_an_independent_writer_and_reader(E, gpu, oracle
     assert sorted(r[3] for r in got) == sorted(r[3] for r in recs)
     assert sorted(r[0] for r in got) == sorted(r[0] for r in recs)       # timestamps travel
     eng.close()
+
+
+@pytest.mark.gpu
+def test_full_arena_drops_puts_but_never_corrupts(E, gpu, oracle):
+    """An arena that runs full with records of mixed sizes: a put that does not fit is dropped (a
+    full LMDB map drops it, filemap.c:143-145,154-157) and every key that still HITs returns its
+    own page byte for byte.  The bump pointer is never rolled back (it saturates until the arena is
+    compacted), so no allocation can ever overlap a record that was stored."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, os
+sys.path.insert(0, os.getcwd())
+import numpy as np, edge_fuse_b200 as E
+n = 2048
+# arena: ~40 % of what the mixed batch needs -> many drops, small records keep fitting near the end
+eng = E.Engine(pshift=16, accel=12, capacity=8192, arena_bytes=int(os.environ["ARENA"]), max_batch=512)
+u = np.full(n, 11, dtype=np.uint64); l = np.arange(n, dtype=np.uint64)
+# incompressible (66 KiB records) interleaved with zero pages (~300-byte records) and text pages
+cids = np.array([8 * c + (0, 2, 1, 2)[c & 3] for c in range(n)], dtype=np.uint64)
+pages = np.stack([E.gen_chunk_host(3, int(c), 65536) for c in cids])
+for rep in range(3):                       # the later rounds run against an arena that is already full
+    lens = eng.put(u, l, pages)
+    out, st = eng.get(u, l)
+    hit = st == E.HIT
+    assert (out[hit] == pages[hit]).all(), "a HIT returned another page's bytes"
+    assert ((st == E.HIT) | (st == E.MISS)).all()
+    stats = eng.stats()
+    assert stats["dropped_puts"] > 0 and stats["arena_used"] <= stats["arena_bytes"]
+    assert stats["entries"] == int(hit.sum())
+assert 0 < hit.sum() < n
+print("full arena ok", int(hit.sum()), stats["dropped_puts"])
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for arena, seg in ((24 << 20, "0"), (40 << 20, "320")):                     # staged path / per-warp segments
+        env = dict(os.environ, ARENA=str(arena), CMB200_SEG_KB=seg)
+        out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=900)
+        assert out.returncode == 0 and "full arena ok" in out.stdout, out.stdout + out.stderr
+
+
+@pytest.mark.gpu
+def test_large_batches_at_capacity_stay_at_capacity(E, gpu, tmp_path, monkeypatch):
+    """cachemap_put_batch with far more pages than the store's capacity, repeatedly: eviction runs
+    before every slice of the batch (no fixed number of rounds), entries end within capacity, nothing
+    is dropped, and the newest pages are the ones that survive."""
+    monkeypatch.setenv("CMB200_ARENA_MB", "160")
+    cap = 2048
+    cm = E.Cachemap(str(tmp_path), cap, 12, 12)
+    bs = 4096
+    n = 20000                                              # ~10 x capacity in ONE call
+    pages = np.stack([datagen.make_page("TRZM"[i & 3], bs, i) for i in range(512)])
+    idx = np.arange(n) % 512
+    nh = np.full(n, 21, dtype=np.uint64)
+    gen = np.zeros(n, dtype=np.uint32)
+    for rnd in range(2):
+        off = (np.arange(rnd * n, (rnd + 1) * n, dtype=np.uint64)) << np.uint64(12)
+        cm.put_batch(off, nh, gen, np.ascontiguousarray(pages[idx]))
+        entries = E.lib().filemap_entries(_pages_ptr(cm))
+        assert entries <= cap + cap // 4, entries        # one slice (capacity / 4) of slack at most
+        assert entries >= cap // 2
+    import ctypes
+    from edge_fuse_b200.binding import Stats
+    st = Stats()
+    assert E.lib().cmb200_get_stats(cm.engine_handle(), ctypes.byref(st)) == 0
+    assert st.dropped_puts == 0
+    out, hit = cm.get_batch(off[-256:], nh[-256:], gen[-256:])
+    assert hit.mean() > 0.9 and (out[hit != 0] == pages[idx[-256:]][hit != 0]).all()
+    cm.free()
+
+
+@pytest.mark.gpu
+def test_sampling_a_nearly_empty_table_and_corrupt_snapshots(E, gpu, oracle, tmp_path):
+    """(1) filemap_get_rand's policy equivalent on a table with 3 live slots out of 2^20: the bounded
+    walk gives up and the cooperative scan finds them (k_sample / k_sample_scan).
+    (2) cmb200_load refuses records whose compressed_length disagrees with their length."""
+    eng = E.Engine(pshift=12, accel=12, capacity=1 << 18, arena_bytes=16 << 20, max_batch=256)
+    assert eng.stats()["table_slots"] >= 1 << 20
+    r = datagen.words(77, 64)
+    _, _, ok = eng.sample(r)
+    assert (np.asarray(ok) == 0).all()                    # empty store: no victim
+    pages = np.stack([datagen.make_page("T", 4096, i) for i in range(3)])
+    u = np.full(3, 8, dtype=np.uint64); l = np.array([5, 6, 7], dtype=np.uint64)
+    eng.put(u, l, pages, ts=np.array([10, 20, 30], dtype=np.uint64))
+    addr, ts, ok = eng.sample(r)
+    assert (np.asarray(ok) == 1).all()
+    got = {(int(a[0]), int(a[1]), int(t)) for a, t in zip(np.asarray(addr).reshape(-1, 2), ts)}
+    assert got <= {(8, 5, 10), (8, 6, 20), (8, 7, 30)} and len(got) >= 2
+    # ---- corrupt snapshot ----
+    snap = str(tmp_path / "s.snap")
+    assert eng.save(snap) == 3
+    raw = bytearray(open(snap, "rb").read())
+    # record 0: header 64 B, record header 32 B, then data_prefix {u, l, compressed_length, pad}
+    clen_at = 64 + 32 + 16
+    good = int.from_bytes(raw[clen_at:clen_at + 4], "little", signed=True)
+    assert 0 < good < 4096 + 1024
+    for bad in (-5, good + 7, 0x7fffffff):
+        broken = bytearray(raw)
+        broken[clen_at:clen_at + 4] = int(bad).to_bytes(4, "little", signed=True)
+        p = str(tmp_path / f"bad{bad & 0xffff}.snap")
+        open(p, "wb").write(broken)
+        e2 = E.Engine(pshift=12, accel=12, capacity=4096, arena_bytes=16 << 20, max_batch=256)
+        with pytest.raises(RuntimeError):
+            e2.load(p)
+        out, st = e2.get(u, l)                             # the engine is still usable and holds nothing wrong
+        assert ((st == E.MISS) | ((st == E.HIT) & (out == pages).all(axis=1))).all()
+        e2.close()
+    eng.close()

@@ -1,17 +1,18 @@
 #!/bin/bash
 # Round-2 A/B of the encode kernel organisations on one B200 (run under gpurun).
 # Each variant runs in its own process (the selectors are read once per process).
+# CMB200_ENC_MODE: 0 lean loop / L1, 2 lean loop / TMA ring, 3 round-1 loop, 1 8-lane groups.
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 CH=${CH:-8192}
+OUT=gpurun_out/${OUT:-r2_variants.txt}
 run() {  # name, env...
   name=$1; shift
-  echo "=== $name" | tee -a gpurun_out/r2_variants.txt
-  env "$@" timeout 300 python tools/kernel_bench.py --chunks $CH --classes ${CLASSES:-TMRZB} --reps 3 2>&1 | tee -a gpurun_out/r2_variants.txt
+  echo "=== $name" | tee -a $OUT
+  env "$@" timeout 300 python tools/kernel_bench.py --chunks $CH --classes ${CLASSES:-TMRZB} --reps 3 2>&1 | tee -a $OUT
 }
-: > gpurun_out/r2_variants.txt
-run plain_l1        CMB200_ENC_MODE=0 CMB200_FP_NOALLOC=0
-run plain_fpna      CMB200_ENC_MODE=0 CMB200_FP_NOALLOC=1
-run ring_l1         CMB200_ENC_MODE=2 CMB200_FP_NOALLOC=0
-run ring_fpna       CMB200_ENC_MODE=2 CMB200_FP_NOALLOC=1
-run ring_fpna_12w   CMB200_ENC_MODE=2 CMB200_FP_NOALLOC=1 CMB200_RING_WARPS=12
+: > $OUT
+for v in ${VARIANTS:-r1:3:0 lean:0:0 lean_fpna:0:1 ring:2:0 ring_fpna:2:1}; do
+  IFS=: read name mode fpna <<< "$v"
+  run $name CMB200_ENC_MODE=$mode CMB200_FP_NOALLOC=$fpna
+done
