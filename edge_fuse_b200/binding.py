@@ -32,6 +32,7 @@ EXPORTED_SYMBOLS = [
     "cmb200_read_fingerprints", "cmb200_get_stats", "cmb200_compose_keys",
     "cmb200_set_stream_order", "cmb200_import_remote", "cmb200_locate_batch", "cmb200_save", "cmb200_load",
     "cmb200_put_step", "cmb200_import_records_dev", "cmb200_compact",
+    "cmb200_get_small", "cmb200_arena_ipc_handle", "cmb200_open_peer",
     "cmb200_lz4_encode_batch", "cmb200_lz4_decode_batch", "cmb200_fingerprint_batch", "cmb200_fingerprint_dev",
     "cmb200_gen_chunk_host", "cmb200_gen_chunks_dev", "cmb200_gen_stream_ids", "cmb200_gen_addr",
 ]
@@ -121,7 +122,10 @@ def lib() -> C.CDLL:
         "cmb200_read_fingerprints": (i32, [vp, sz, vp, vp, vp]),
         "cmb200_get_stats": (i32, [vp, vp]),
         "cmb200_set_stream_order": (i32, [vp, u64, u64]),
-        "cmb200_import_remote": (i32, [vp, sz, vp, vp, vp, i32]),
+        "cmb200_import_remote": (i32, [vp, sz, vp, vp, vp, vp, i32]),
+        "cmb200_get_small": (i32, [vp, sz, vp, vp, vp]),
+        "cmb200_arena_ipc_handle": (i32, [vp, vp, vp]),
+        "cmb200_open_peer": (i32, [vp, C.c_uint32, vp, C.c_uint64]),
         "cmb200_locate_batch": (i32, [vp, sz, vp, vp, vp]),
         "cmb200_compose_keys": (i32, [i32, sz, vp, vp, vp, i32, vp, vp, vp]),
         "cmb200_lz4_encode_batch": (i32, [i32, vp, sz, u32, sz, i32, vp, sz, vp, vp]),
@@ -327,6 +331,38 @@ class Engine:
         _check(fn(self.h, n, _ptr(addr), _ptr(valid), _ptr(out), _ptr(status)), "cmb200_get_batch")
         return out, status
 
+    def get_small(self, u, l, out=None):
+        """cmb200_get_small: the fused small-batch get.  `out` = page-locked host pointer / device
+        pointer (int) or None (a page-locked buffer is allocated and copied into a numpy array)."""
+        addr = _addr_array(u, l)
+        n = len(addr)
+        status = np.zeros(n, dtype=np.int32)
+        own = None
+        if out is None:
+            own = lib().cmb200_host_alloc(max(1, n) * self.bsize)
+            if not own:
+                raise RuntimeError("cmb200_host_alloc failed")
+            out = own
+        try:
+            _check(lib().cmb200_get_small(self.h, n, _ptr(addr), _ptr(out), _ptr(status)), "cmb200_get_small")
+            if own:
+                arr = np.ctypeslib.as_array((C.c_uint8 * (n * self.bsize)).from_address(own)).reshape(n, self.bsize).copy()
+                return arr, status
+            return out, status
+        finally:
+            if own:
+                lib().cmb200_host_free(own)
+
+    def arena_ipc_handle(self):
+        h = (C.c_uint8 * 64)()
+        size = C.c_uint64(0)
+        _check(lib().cmb200_arena_ipc_handle(self.h, h, C.byref(size)), "cmb200_arena_ipc_handle")
+        return bytes(h), int(size.value)
+
+    def open_peer(self, rank: int, handle: bytes, arena_bytes: int):
+        buf = (C.c_uint8 * 64).from_buffer_copy(handle)
+        _check(lib().cmb200_open_peer(self.h, rank, buf, arena_bytes), "cmb200_open_peer")
+
     def unset(self, u, l):
         addr = _addr_array(u, l)
         _check(lib().cmb200_unset_batch(self.h, len(addr), _ptr(addr)), "cmb200_unset_batch")
@@ -387,11 +423,12 @@ class Engine:
     def set_stream_order(self, next_seq: int, stride: int):
         _check(lib().cmb200_set_stream_order(self.h, next_seq, stride), "cmb200_set_stream_order")
 
-    def import_remote(self, u, l, owner, seq):
+    def import_remote(self, u, l, owner, seq, loc=None):
         addr = _addr_array(u, l)
         owner = np.ascontiguousarray(owner, dtype=np.uint32)
         seq = np.ascontiguousarray(seq, dtype=np.uint64)
-        _check(lib().cmb200_import_remote(self.h, len(addr), _ptr(addr), _ptr(owner), _ptr(seq), 0),
+        loc = None if loc is None else np.ascontiguousarray(loc, dtype=np.uint64)
+        _check(lib().cmb200_import_remote(self.h, len(addr), _ptr(addr), _ptr(owner), _ptr(seq), _ptr(loc), 0),
                "cmb200_import_remote")
 
     def locate(self, u, l):

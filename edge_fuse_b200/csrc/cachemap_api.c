@@ -44,6 +44,8 @@ struct fm_req {
 	cmb200_addr addr;
 	void *out;              /* REQ_GET: malloc()ed page (or dst) on a hit, else NULL */
 	void *dst;              /* REQ_GET: caller's buffer to fill instead of malloc()ing one */
+	const uint8_t *staged;  /* REQ_GET hit: the page in the leader's stage buffer, copied out by the waiter itself */
+	int stage_buf;          /* which stage buffer `staged` points into */
 	int bad_entry;
 	int done;
 	struct fm_req *next;
@@ -66,7 +68,9 @@ struct filemap {
 	pthread_mutex_t init_mu;
 	int init_state;         /* 0 = not yet, 1 = ready, -1 = failed */
 	cmb200_engine *eng;
-	uint8_t *h_stage;       /* page-locked, COMBINE_MAX pages (get results) */
+	uint8_t *h_stage;       /* page-locked, 2 x COMBINE_MAX pages (get results, two batches alternate) */
+	int stage_turn;         /* stage buffer of the next batch (leader only) */
+	int stage_readers[2];   /* waiters still copying their page out of each buffer (under q_mu) */
 	/* combining queue (gets, unsets) */
 	pthread_mutex_t q_mu;
 	pthread_cond_t q_cv;
@@ -123,7 +127,7 @@ filemap_engine_ready(struct filemap *m)
 		cfg.flags = env_long("CMB200_FINGERPRINT", 0) ? CMB200_FINGERPRINT : 0;
 		m->eng = cmb200_engine_create(&cfg);
 		if (m->eng) {
-			m->h_stage = cmb200_host_alloc((size_t)COMBINE_MAX * m->bsize);
+			m->h_stage = cmb200_host_alloc((size_t)2 * COMBINE_MAX * m->bsize);
 			/* ring of ~64 MiB by default, at least 64 pages */
 			long slots = env_long("CMB200_WB_SLOTS", (64L << 20) / m->bsize);
 			if (slots > 0 && slots < 64)
@@ -495,13 +499,29 @@ filemap_run_batch(struct filemap *m, struct fm_req **reqs, int count)
 		idx[k] = i;
 		k++;
 	}
-	if (k && cmb200_get_batch(m->eng, (size_t)k, addr, NULL, m->h_stage, status) == 0) {
+	/* the fused small-batch get: one kernel on the get stream, pages land in a page-locked stage
+	 * buffer directly; page sizes it does not serve (> 64 KiB) take the two-kernel batch path.
+	 * The hits are NOT copied here: every waiter copies its own page out of the stage when it wakes
+	 * up (filemap_submit_many), so a batch of k pages costs the leader no k memcpys; the two stage
+	 * buffers alternate, and a buffer is reused only when its waiters are done with it. */
+	const int sb = m->stage_turn;
+	m->stage_turn ^= 1;
+	uint8_t *stage = m->h_stage + (size_t)sb * COMBINE_MAX * (size_t)m->bsize;
+	if (k) {
+		pthread_mutex_lock(&m->q_mu);
+		while (m->stage_readers[sb] > 0)
+			pthread_cond_wait(&m->q_cv, &m->q_mu);
+		pthread_mutex_unlock(&m->q_mu);
+	}
+	int rc = k ? cmb200_get_small(m->eng, (size_t)k, addr, stage, status) : 0;
+	if (k && rc == -2)
+		rc = cmb200_get_batch(m->eng, (size_t)k, addr, NULL, stage, status);
+	if (k && rc == 0) {
 		for (int j = 0; j < k; j++) {
 			struct fm_req *r = reqs[idx[j]];
 			if (status[j] == CMB200_HIT) {
-				r->out = r->dst ? r->dst : malloc((size_t)m->bsize);    /* filemap.c:242 */
-				if (r->out)
-					memcpy(r->out, m->h_stage + (size_t)j * m->bsize, (size_t)m->bsize);
+				r->staged = stage + (size_t)j * m->bsize;
+				r->stage_buf = sb;
 			} else if (status[j] == CMB200_BAD_ENTRY) {
 				r->bad_entry = 1;
 			}
@@ -511,11 +531,37 @@ filemap_run_batch(struct filemap *m, struct fm_req **reqs, int count)
 
 /* Queues `count` requests (an array) and returns when all of them have been served.  The queue is
  * FIFO and batches complete in order, so the last request finishing means all have. */
+/* Copies the pages of the caller's own finished requests out of the stage buffers and releases
+ * them.  Called without q_mu. */
+static void
+filemap_copy_out(struct filemap *m, struct fm_req *reqs, int count)
+{
+	int released[2] = { 0, 0 };
+	for (int i = 0; i < count; i++) {
+		struct fm_req *r = &reqs[i];
+		if (!r->staged)
+			continue;
+		r->out = r->dst ? r->dst : malloc((size_t)m->bsize);    /* filemap.c:242 */
+		if (r->out)
+			memcpy(r->out, r->staged, (size_t)m->bsize);
+		released[r->stage_buf]++;
+		r->staged = NULL;
+	}
+	if (released[0] || released[1]) {
+		pthread_mutex_lock(&m->q_mu);
+		m->stage_readers[0] -= released[0];
+		m->stage_readers[1] -= released[1];
+		pthread_cond_broadcast(&m->q_cv);
+		pthread_mutex_unlock(&m->q_mu);
+	}
+}
+
 static void
 filemap_submit_many(struct filemap *m, struct fm_req *reqs, int count)
 {
 	for (int i = 0; i < count; i++) {
 		reqs[i].done = 0;
+		reqs[i].staged = NULL;
 		reqs[i].next = i + 1 < count ? &reqs[i + 1] : NULL;
 	}
 	struct fm_req *req = &reqs[count - 1];
@@ -531,23 +577,32 @@ filemap_submit_many(struct filemap *m, struct fm_req *reqs, int count)
 			continue;
 		}
 		struct fm_req *batch[COMBINE_MAX];
-		int count = 0;
+		int nb = 0;
 		m->leader_active = 1;
-		while (m->q_head && count < COMBINE_MAX) {
-			batch[count++] = m->q_head;
+		while (m->q_head && nb < COMBINE_MAX) {
+			batch[nb++] = m->q_head;
 			m->q_head = m->q_head->next;
 		}
 		if (!m->q_head)
 			m->q_tail = NULL;
 		pthread_mutex_unlock(&m->q_mu);
-		filemap_run_batch(m, batch, count);
+		/* a long request chain spans several batches: take my pages of the earlier ones out first,
+		 * the batch I am about to run may need their stage buffer */
+		filemap_copy_out(m, reqs, count);
+		filemap_run_batch(m, batch, nb);
 		pthread_mutex_lock(&m->q_mu);
-		for (int i = 0; i < count; i++)
+		for (int i = 0; i < nb; i++) {
+			if (batch[i]->staged)
+				m->stage_readers[batch[i]->stage_buf]++;
 			batch[i]->done = 1;
+		}
 		m->leader_active = 0;
 		pthread_cond_broadcast(&m->q_cv);
 	}
 	pthread_mutex_unlock(&m->q_mu);
+	/* every caller copies the pages of ITS requests out of the stage (in parallel with the other
+	 * callers and with the next batch's kernel), then releases the stage buffer */
+	filemap_copy_out(m, reqs, count);
 }
 
 static void

@@ -40,6 +40,18 @@ struct cmb200_engine {
 	uint32_t host_batch = 4096;  // chunks per H2D/D2H pipeline step (page ring size), <= max_batch
 	uint32_t flags = 0;
 	cudaStream_t st = nullptr, copy = nullptr;
+	// small gets (cmb200_get_small) have their own stream, lock and buffers: they neither queue behind
+	// a put batch on `st` nor take `mu`
+	cudaStream_t gst = nullptr;
+	std::mutex get_mu;
+	unsigned long long *d_gaddr = nullptr;
+	int32_t *h_gstatus = nullptr;                // page-locked, the kernel writes it directly
+	cmb200_addr *h_gaddr = nullptr;
+	static constexpr size_t GET_SMALL_MAX = 1024;
+	const uint8_t *peer_base[GET_MAX_PEERS] = {};
+	uint64_t peer_size[GET_MAX_PEERS] = {};
+	uint64_t small_get_requests = 0, small_get_hits = 0, small_get_launches = 0;
+	unsigned long long *d_recoff_out = nullptr;  // arena offset per chunk of the current put slice (exchange records)
 	cudaEvent_t landed[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr};
 	TableView table{};
 	ArenaView arena{};
@@ -120,6 +132,11 @@ extern "C" void cmb200_engine_destroy(cmb200_engine *e) {
 	cudaFree(e->d_pages[0]); cudaFree(e->d_pages[1]); cudaFree(e->d_stage);
 	cudaFree(e->d_addr); cudaFree(e->d_ts); cudaFree(e->d_valid); cudaFree(e->d_slot); cudaFree(e->d_vlen);
 	if (e->h_meta) cudaFreeHost(e->h_meta);
+	if (e->h_gstatus) cudaFreeHost(e->h_gstatus);
+	if (e->h_gaddr) cudaFreeHost(e->h_gaddr);
+	cudaFree(e->d_gaddr); cudaFree(e->d_recoff_out);
+	for (int r = 0; r < GET_MAX_PEERS; r++) if (e->peer_base[r]) cudaIpcCloseMemHandle((void *)e->peer_base[r]);
+	if (e->gst) { cudaStreamSynchronize(e->gst); cudaStreamDestroy(e->gst); }
 	cudaFree(e->d_lens); cudaFree(e->d_status); cudaFree(e->d_fps); cudaFree(e->d_recoff); cudaFree(e->d_work); cudaFree(e->d_import_slot);
 	for (int i = 0; i < 2; i++) {
 		if (e->landed[i]) cudaEventDestroy(e->landed[i]);
@@ -168,6 +185,7 @@ extern "C" cmb200_engine *cmb200_engine_create(const cmb200_config *cfg) {
 		e->table.cap = slots;
 		ENG_CHECK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
 		ENG_CHECK(cudaStreamCreateWithFlags(&e->copy, cudaStreamNonBlocking));
+		ENG_CHECK(cudaStreamCreateWithFlags(&e->gst, cudaStreamNonBlocking));
 		for (int i = 0; i < 2; i++) {
 			ENG_CHECK(cudaEventCreateWithFlags(&e->landed[i], cudaEventDisableTiming));
 			ENG_CHECK(cudaEventCreateWithFlags(&e->consumed[i], cudaEventDisableTiming));
@@ -220,6 +238,10 @@ extern "C" cmb200_engine *cmb200_engine_create(const cmb200_config *cfg) {
 		ENG_CHECK(cudaMalloc(&e->d_recoff, B * 8));
 		ENG_CHECK(cudaMalloc(&e->d_work, 64));
 		ENG_CHECK(cudaMallocHost(&e->h_meta, cmb200_engine::META_CAP * 33));
+		ENG_CHECK(cudaMalloc(&e->d_gaddr, cmb200_engine::GET_SMALL_MAX * 16));
+		ENG_CHECK(cudaMallocHost(&e->h_gstatus, cmb200_engine::GET_SMALL_MAX * 4));
+		ENG_CHECK(cudaMallocHost(&e->h_gaddr, cmb200_engine::GET_SMALL_MAX * 16));
+		ENG_CHECK(cudaMalloc(&e->d_recoff_out, M * 8));
 
 		uint64_t arena = cfg->arena_bytes;
 		if (!arena) {
@@ -386,6 +408,7 @@ static int put_slice(cmb200_engine *e, size_t n, const cmb200_addr *addr, const 
 		job.accel = (uint32_t)e->accel;
 		job.stage = e->d_stage; job.stage_stride = e->stage_stride;
 		job.lens = e->d_lens + at;
+		job.rec_out = e->d_recoff_out + at;
 		job.fps = (e->flags & CMB200_FINGERPRINT) ? e->d_fps : nullptr;
 		job.work = e->d_work;
 		job.slot_idx = e->d_slot;
@@ -412,7 +435,7 @@ static int put_slice(cmb200_engine *e, size_t n, const cmb200_addr *addr, const 
 	}
 	e->stats.put_chunks += n;
 	if (recs && recs->out) {
-		if (launch_pack_records(d_addr, e->d_lens, (uint32_t)n, seq_first, e->seq_stride, recs->rank, recs->out, e->st)) return -1;
+		if (launch_pack_records(d_addr, e->d_lens, e->d_recoff_out, (uint32_t)n, seq_first, e->seq_stride, recs->rank, recs->out, e->st)) return -1;
 		e->stats.kernel_launches++;
 	}
 	if (copy_meta) CMB_CHECK(cudaEventRecord(e->meta_free[mb], e->st));
@@ -620,24 +643,98 @@ extern "C" int cmb200_set_stream_order(cmb200_engine *e, uint64_t next_seq, uint
 }
 
 extern "C" int cmb200_import_remote(cmb200_engine *e, size_t n, const cmb200_addr *addr, const uint32_t *owner,
-    const uint64_t *seq, int on_dev) {
+    const uint64_t *seq, const uint64_t *loc, int on_dev) {
 	std::lock_guard<std::mutex> g(e->mu);
 	CMB_CHECK(cudaSetDevice(e->device));
 	for (size_t at = 0; at < n; at += e->max_batch) {
 		uint32_t m = (uint32_t)((n - at < e->max_batch) ? n - at : e->max_batch);
-		const unsigned long long *d_a; const uint32_t *d_o; const unsigned long long *d_s;
+		const unsigned long long *d_a; const uint32_t *d_o; const unsigned long long *d_s; const unsigned long long *d_l = nullptr;
 		if (on_dev) {
 			d_a = (const unsigned long long *)(addr + at); d_o = owner + at; d_s = (const unsigned long long *)(seq + at);
+			if (loc) d_l = (const unsigned long long *)(loc + at);
 		} else {
 			CMB_CHECK(cudaMemcpyAsync(e->d_addr, addr + at, (size_t)m * 16, cudaMemcpyHostToDevice, e->st));
 			CMB_CHECK(cudaMemcpyAsync(e->d_vlen, owner + at, (size_t)m * 4, cudaMemcpyHostToDevice, e->st));
 			CMB_CHECK(cudaMemcpyAsync(e->d_ts, seq + at, (size_t)m * 8, cudaMemcpyHostToDevice, e->st));
-			d_a = e->d_addr; d_o = e->d_vlen; d_s = e->d_ts;
+			if (loc) CMB_CHECK(cudaMemcpyAsync(e->d_recoff, loc + at, (size_t)m * 8, cudaMemcpyHostToDevice, e->st));
+			d_a = e->d_addr; d_o = e->d_vlen; d_s = e->d_ts; d_l = loc ? (const unsigned long long *)e->d_recoff : nullptr;
 		}
-		if (launch_import(e->table, e->arena, d_a, d_o, d_s, m, e->d_slot, e->st)) return -1;
+		if (launch_import(e->table, e->arena, d_a, d_o, d_s, d_l, m, e->d_slot, e->st)) return -1;
 		e->stats.kernel_launches += 2;
 	}
 	CMB_CHECK(cudaStreamSynchronize(e->st));
+	return 0;
+}
+
+// ---- small gets: one fused kernel on their own stream ------------------------------------------
+
+extern "C" int cmb200_get_small(cmb200_engine *e, size_t n, const cmb200_addr *addr, void *pages_out, int32_t *status_out) {
+	if (n == 0) return 0;
+	if (!get_small_supports(e->bsize)) { set_error_msg("cmb200_get_small: page size not supported by the fused kernel"); return -2; }
+	std::lock_guard<std::mutex> g(e->get_mu);
+	CMB_CHECK(cudaSetDevice(e->device));
+	static const int32_t PENDING = -1;
+	for (size_t at = 0; at < n; at += cmb200_engine::GET_SMALL_MAX) {
+		const uint32_t m = (uint32_t)((n - at < cmb200_engine::GET_SMALL_MAX) ? n - at : cmb200_engine::GET_SMALL_MAX);
+		// Requests and answers travel through page-locked host memory that the kernel reads and writes
+		// directly: no copy is queued before or after the launch, and the caller learns of the end by
+		// watching the status words flip (the kernel writes a page, fences, then its status), which costs
+		// a few microseconds where a stream synchronisation costs tens.
+		memcpy(e->h_gaddr, addr + at, (size_t)m * 16);
+		for (uint32_t i = 0; i < m; i++) ((volatile int32_t *)e->h_gstatus)[i] = PENDING;
+		GetJob job{};
+		job.table = e->table; job.arena = e->arena.base; job.arena_size = e->arena.size;
+		job.addr = (const unsigned long long *)e->h_gaddr; job.valid = nullptr; job.n = m; job.nbytes = e->bsize;
+		job.out = (uint8_t *)pages_out + at * e->bsize;          // device memory or page-locked host memory (UVA)
+		job.status = e->h_gstatus;
+		for (int r = 0; r < GET_MAX_PEERS; r++) { job.peer[r] = e->peer_base[r]; job.peer_size[r] = e->peer_size[r]; }
+		if (launch_get_small(job, e->gst)) return -1;
+		uint32_t done = 0;
+		for (uint64_t spins = 0; done < m;) {
+			if (((volatile int32_t *)e->h_gstatus)[done] != PENDING) { done++; continue; }
+#if defined(__x86_64__)
+			__builtin_ia32_pause();
+#endif
+			if (++spins > 20000) {                                // ~1 ms of polling: a large batch, let the driver wait
+				CMB_CHECK(cudaStreamSynchronize(e->gst));
+				spins = 0;
+				if (((volatile int32_t *)e->h_gstatus)[done] == PENDING) { set_error_msg("cmb200_get_small: kernel finished without an answer"); return -1; }
+			}
+		}
+		__atomic_thread_fence(__ATOMIC_ACQUIRE);
+		memcpy(status_out + at, e->h_gstatus, (size_t)m * 4);
+		e->small_get_launches++;
+		for (uint32_t i = 0; i < m; i++) {
+			if (status_out[at + i] != CMB200_INVALID) e->small_get_requests++;
+			if (status_out[at + i] == CMB200_HIT) e->small_get_hits++;
+		}
+	}
+	return 0;
+}
+
+// ---- peers: the other ranks' arenas, mapped for NVLink reads -------------------------------------
+
+extern "C" int cmb200_arena_ipc_handle(cmb200_engine *e, void *handle64, uint64_t *arena_bytes_out) {
+	CMB_CHECK(cudaSetDevice(e->device));
+	cudaIpcMemHandle_t h;
+	static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+	CMB_CHECK(cudaIpcGetMemHandle(&h, e->arena.base));
+	memcpy(handle64, &h, 64);
+	if (arena_bytes_out) *arena_bytes_out = e->arena.size;
+	return 0;
+}
+
+extern "C" int cmb200_open_peer(cmb200_engine *e, uint32_t rank, const void *handle64, uint64_t arena_bytes) {
+	if (rank >= GET_MAX_PEERS) { set_error_msg("cmb200_open_peer: rank out of range"); return -1; }
+	std::lock_guard<std::mutex> g(e->get_mu);
+	CMB_CHECK(cudaSetDevice(e->device));
+	cudaIpcMemHandle_t h;
+	memcpy(&h, handle64, 64);
+	void *p = nullptr;
+	CMB_CHECK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+	if (e->peer_base[rank]) cudaIpcCloseMemHandle((void *)e->peer_base[rank]);
+	e->peer_base[rank] = (const uint8_t *)p;
+	e->peer_size[rank] = arena_bytes;
 	return 0;
 }
 
@@ -676,6 +773,11 @@ extern "C" int cmb200_get_stats(cmb200_engine *e, cmb200_stats *out) {
 	if (read_counters(e, c)) return -1;
 	harvest_pending(e, true);
 	*out = e->stats;
+	{
+		std::lock_guard<std::mutex> gg(e->get_mu);
+		out->get_requests += e->small_get_requests; out->get_hits += e->small_get_hits;
+		out->kernel_launches += e->small_get_launches;
+	}
 	out->entries = c[0]; out->tombstones = c[1];
 	out->arena_used = c[2] < e->arena.size ? c[2] : e->arena.size;   // the bump pointer saturates past the end (no rollback)
 	out->arena_garbage = c[3];
@@ -908,6 +1010,7 @@ extern "C" int cmb200_load(cmb200_engine *e, const char *path, uint64_t *records
 // to overflow although a good part of it is garbage (filemap_make_room, cmb200_compact).
 extern "C" int cmb200_compact(cmb200_engine *e, uint64_t *reclaimed_out) {
 	std::lock_guard<std::mutex> g(e->mu);
+	std::lock_guard<std::mutex> gg(e->get_mu);       // records move: no small get may be reading the arena
 	unsigned long long c[8];
 	if (read_counters(e, c)) return -1;
 	harvest_pending(e, true);

@@ -241,6 +241,24 @@ __global__ void __launch_bounds__(256) k_sample_scan(TableView t, const unsigned
 // fused fingerprint -> LZ4 encode -> arena commit
 // ------------------------------------------------------------------------------------------
 
+// Points the slot at a finished record (one thread).  Order: location first, then the length that
+// makes the slot valid; readers on other streams take the length and the address from the record's
+// own prefix and only the location from the slot (k_get_small).
+__device__ __forceinline__ void slot_publish(const EncodeJob &job, Slot &s, uint32_t i, uint32_t idx, unsigned long long off,
+    uint32_t need, uint32_t clen, unsigned long long au, unsigned long long al, uint64_t fp_hi, uint64_t fp_lo) {
+	if (s.owner) { atomicAdd(job.table.remote, (unsigned long long)-1ll); s.owner = 0; }   // now newest here (alloc held the remote length)
+	else if (s.alloc) atomicAdd(job.arena.garbage, (unsigned long long)s.alloc);         // the record this one replaces
+	s.addr_u = au; s.addr_l = al;
+	s.ts = job.ts ? job.ts[i] : 0;
+	if (job.table.fp) { job.table.fp[2 * (size_t)idx] = fp_hi; job.table.fp[2 * (size_t)idx + 1] = fp_lo; }
+	s.alloc = need;
+	*reinterpret_cast<volatile unsigned long long *>(&s.rec_off) = off;
+	__threadfence();
+	if (s.vlen == 0) atomicAdd(job.table.entries, 1ull);
+	*reinterpret_cast<volatile uint32_t *>(&s.vlen) = clen + 1u;
+	if (job.rec_out) job.rec_out[i] = off;
+}
+
 // Stores the finished block as a filemap record {data_prefix, block} (filemap.c:140-147) and
 // publishes it in the key table.  Called by the whole warp; lane 0 owns the bookkeeping.
 __device__ void commit_record(const EncodeJob &job, uint32_t i, uint32_t idx, const uint8_t *payload,
@@ -250,27 +268,24 @@ __device__ void commit_record(const EncodeJob &job, uint32_t i, uint32_t idx, co
 	unsigned long long off = 0;
 	int ok = 1;
 	if (lane == 0) {
-		if (s.alloc >= need) {
-			off = s.rec_off;                         // rewrite in place
-		} else {
-			if (s.alloc) atomicAdd(job.arena.garbage, (unsigned long long)s.alloc);
-			off = atomicAdd(job.arena.head, (unsigned long long)need);
-			if (off + need > job.arena.size) {
-				// arena full: the put is dropped silently, as a full LMDB map drops it
-				// (filemap.c:143-145,154-157).  The bump pointer is never rolled back (a rollback
-				// races with allocations that succeeded in between and would hand their bytes out
-				// twice): it stays saturated until cmb200_compact resets it.
-				atomicAdd(job.arena.dropped, 1ull);
-				if (s.vlen) atomicAdd(job.table.entries, (unsigned long long)-1ll);
-				s.vlen = 0; s.alloc = 0;
-				ok = 0;
-			} else {
-				s.alloc = need; s.rec_off = off;
-			}
+		// Records are immutable once published and a rewrite never reuses the old record's bytes:
+		// a get that runs concurrently on another stream (k_get_small) decodes either the old or the
+		// new record, never a torn one (LMDB gives the reference's readers a snapshot, filemap.c:223).
+		// The old bytes become garbage until the arena is compacted.
+		off = atomicAdd(job.arena.head, (unsigned long long)need);
+		if (off + need > job.arena.size) {
+			// arena full: the put is dropped silently, as a full LMDB map drops it
+			// (filemap.c:143-145,154-157).  The bump pointer is never rolled back (a rollback
+			// races with allocations that succeeded in between and would hand their bytes out
+			// twice): it stays saturated until cmb200_compact resets it.
+			// The slot is left as it is: a record the key already has stays readable, as the
+			// reference's store keeps the old value when mdb_put fails.
+			atomicAdd(job.arena.dropped, 1ull);
+			ok = 0;
 		}
 	}
 	ok = __shfl_sync(CMB_FULL, ok, 0);
-	if (!ok) return;
+	if (!ok) { if (lane == 0 && job.rec_out) job.rec_out[i] = ~0ull; return; }
 	off = __shfl_sync(CMB_FULL, off, 0);
 	uint8_t *rec = job.arena.base + off;
 	const unsigned long long au = job.addr[2 * i], al = job.addr[2 * i + 1];
@@ -288,54 +303,28 @@ __device__ void commit_record(const EncodeJob &job, uint32_t i, uint32_t idx, co
 	}
 	if (payload_ro) warp_copy_ro(rec + 24, payload, plen, lane);
 	else warp_copy_rw(rec + 24, payload, plen, lane);
+	__threadfence();                                 // the record is complete before the slot points to it
 	__syncwarp();
-	if (lane == 0) {
-		if (s.owner) { atomicAdd(job.table.remote, (unsigned long long)-1ll); s.owner = 0; }   // now newest here
-		s.addr_u = au; s.addr_l = al;
-		s.ts = job.ts ? job.ts[i] : 0;
-		if (job.table.fp) { job.table.fp[2 * (size_t)idx] = fp_hi; job.table.fp[2 * (size_t)idx + 1] = fp_lo; }
-		if (s.vlen == 0) atomicAdd(job.table.entries, 1ull);
-		s.vlen = (uint32_t)clen + 1u;
-	}
+	if (lane == 0) slot_publish(job, s, i, idx, off, need, (uint32_t)clen, au, al, fp_hi, fp_lo);
 }
 
 // Direct variant of commit_record: the block already sits in the arena at `base + 24` (this warp's
-// segment cursor).  A new key simply keeps it there; a rewrite whose old record is large enough is
-// copied over the old record so that rewrites do not consume arena.  Returns the bytes of the
-// segment consumed (0 when the old record was reused).
+// segment cursor) and stays there.  Returns the bytes of the segment consumed.
 __device__ uint32_t commit_direct(const EncodeJob &job, uint32_t i, uint32_t idx, unsigned long long base,
     uint32_t clen, uint64_t fp_hi, uint64_t fp_lo, int lane) {
 	Slot &s = job.table.slots[idx];
 	const uint32_t need = (24u + clen + 15u) & ~15u;
-	unsigned long long rec = base;
-	int reuse = 0;
-	if (lane == 0) {
-		if (s.alloc >= need) { rec = s.rec_off; reuse = 1; }
-		else {
-			if (s.alloc) atomicAdd(job.arena.garbage, (unsigned long long)s.alloc);
-			s.alloc = need; s.rec_off = base;
-		}
-	}
-	reuse = __shfl_sync(CMB_FULL, reuse, 0);
-	rec = __shfl_sync(CMB_FULL, rec, 0);
-	uint8_t *r = job.arena.base + rec;
-	if (reuse) { warp_copy_rw(r + 24, job.arena.base + base + 24, clen, lane); }
+	uint8_t *r = job.arena.base + base;
 	const unsigned long long au = job.addr[2 * i], al = job.addr[2 * i + 1];
 	if (lane < 6) {
 		const uint32_t w = lane == 0 ? (uint32_t)au : lane == 1 ? (uint32_t)(au >> 32) : lane == 2 ? (uint32_t)al
 		    : lane == 3 ? (uint32_t)(al >> 32) : lane == 4 ? clen : 0u;
 		reinterpret_cast<uint32_t *>(r)[lane] = w;
 	}
+	__threadfence();                                 // block (written by all lanes) and prefix before the slot
 	__syncwarp();
-	if (lane == 0) {
-		if (s.owner) { atomicAdd(job.table.remote, (unsigned long long)-1ll); s.owner = 0; }
-		s.addr_u = au; s.addr_l = al;
-		s.ts = job.ts ? job.ts[i] : 0;
-		if (job.table.fp) { job.table.fp[2 * (size_t)idx] = fp_hi; job.table.fp[2 * (size_t)idx + 1] = fp_lo; }
-		if (s.vlen == 0) atomicAdd(job.table.entries, 1ull);
-		s.vlen = clen + 1u;
-	}
-	return reuse ? 0u : need;
+	if (lane == 0) slot_publish(job, s, i, idx, base, need, clen, au, al, fp_hi, fp_lo);
+	return need;
 }
 
 // ENC 0: lean loop, page read through the L1.  ENC 1: lean loop, parse frontier staged in a per-warp
@@ -443,23 +432,14 @@ __device__ void grp_commit_record(const GroupCtx &g, const EncodeJob &job, uint3
 	unsigned long long off = 0;
 	int ok = 1;
 	if (g.gl == 0) {
-		if (s.alloc >= need) {
-			off = s.rec_off;
-		} else {
-			if (s.alloc) atomicAdd(job.arena.garbage, (unsigned long long)s.alloc);
-			off = atomicAdd(job.arena.head, (unsigned long long)need);
-			if (off + need > job.arena.size) {
-				atomicAdd(job.arena.dropped, 1ull);      // no rollback, see commit_record
-				if (s.vlen) atomicAdd(job.table.entries, (unsigned long long)-1ll);
-				s.vlen = 0; s.alloc = 0;
-				ok = 0;
-			} else {
-				s.alloc = need; s.rec_off = off;
-			}
+		off = atomicAdd(job.arena.head, (unsigned long long)need);
+		if (off + need > job.arena.size) {
+			atomicAdd(job.arena.dropped, 1ull);      // no rollback, slot untouched: see commit_record
+			ok = 0;
 		}
 	}
 	ok = grp_shfl(g, ok, 0);
-	if (!ok) return;
+	if (!ok) { if (g.gl == 0 && job.rec_out) job.rec_out[i] = ~0ull; return; }
 	off = grp_shfl(g, off, 0);
 	uint8_t *rec = job.arena.base + off;
 	const unsigned long long au = job.addr[2 * i], al = job.addr[2 * i + 1];
@@ -470,15 +450,11 @@ __device__ void grp_commit_record(const GroupCtx &g, const EncodeJob &job, uint3
 	}
 	if (payload_ro) grp_copy<true>(g, rec + 24, payload, plen);
 	else grp_copy<false>(g, rec + 24, payload, plen);
+	__threadfence();
 	__syncwarp(g.gmask);
-	if (g.gl == 0) {
-		if (s.owner) { atomicAdd(job.table.remote, (unsigned long long)-1ll); s.owner = 0; }
-		s.addr_u = au; s.addr_l = al;
-		s.ts = job.ts ? job.ts[i] : 0;
-		if (job.table.fp && job.fps) { job.table.fp[2 * (size_t)idx] = job.fps[2 * (size_t)i]; job.table.fp[2 * (size_t)idx + 1] = job.fps[2 * (size_t)i + 1]; }
-		if (s.vlen == 0) atomicAdd(job.table.entries, 1ull);
-		s.vlen = (uint32_t)clen + 1u;
-	}
+	if (g.gl == 0)
+		slot_publish(job, s, i, idx, off, need, (uint32_t)clen, au, al, job.fps ? job.fps[2 * (size_t)i] : 0ull,
+		    job.fps ? job.fps[2 * (size_t)i + 1] : 0ull);
 }
 
 template <bool WIDE>
@@ -769,6 +745,158 @@ int launch_decode(const DecodeJob &job, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------
+// fused small-batch get: lookup + record staging (TMA) + decode in shared memory + page out
+// ------------------------------------------------------------------------------------------
+
+constexpr uint32_t GS_THREADS = 128;
+constexpr uint32_t GS_CTRL = 128 + 1152;          // control block + decode pipeline ring at the start of the shared memory
+static_assert(sizeof(DecodePipe) <= 1152, "decode pipe fits its slot");
+constexpr uint32_t GS_MAX_PAGE = 65536;           // record buffer + page buffer must fit 227 KiB
+struct GetShared {
+	unsigned long long bar;                   // mbarrier of the record copy
+	unsigned long long off;                   // arena offset of the record
+	int32_t st;
+	uint32_t clen;                            // expected compressed_length (0 = raw page)
+	uint32_t owner;                           // rank + 1 when the record is in a peer's arena
+	int32_t used;
+};
+__host__ __device__ inline uint32_t gs_recbuf(uint32_t nbytes) { return (24u + nbytes + 1024u + 31u) & ~15u; }
+bool get_small_supports(uint32_t nbytes) { return nbytes >= 64u && nbytes <= GS_MAX_PAGE && (nbytes & 15u) == 0; }
+
+__device__ __forceinline__ unsigned long long ldv64(const unsigned long long *p) { return *reinterpret_cast<const volatile unsigned long long *>(p); }
+__device__ __forceinline__ uint32_t ldv32(const uint32_t *p) { return *reinterpret_cast<const volatile uint32_t *>(p); }
+
+// Reads the slot of {u, l}.  Readers never block writers: the location is a single 8-byte load and
+// everything else about the record (address, length) is taken from the record's own prefix later.
+__device__ void gs_lookup(const GetJob &job, unsigned long long u, unsigned long long l, GetShared *sh) {
+	int32_t st = ST_MISS;
+	uint32_t clen = 0, owner = 0;
+	unsigned long long off = 0;
+	const uint32_t idx = table_find(job.table, fnv_addr(u, l));
+	if (idx != 0xffffffffu) {
+		const Slot *s = &job.table.slots[idx];
+		const uint32_t vlen = ldv32(&s->vlen);
+		const unsigned long long au = ldv64(&s->addr_u), al = ldv64(&s->addr_l);
+		if (vlen != 0u) {
+			if (au == u && al == l) { st = ST_HIT; __threadfence(); off = ldv64(&s->rec_off); clen = vlen - 1u; }
+			else st = ST_BAD_ENTRY;                              // filemap.c:236-240
+		} else {
+			const unsigned long long ow = ldv64(&s->owner);
+			if (ow != 0ull && au == u && al == l) {
+				st = ST_REMOTE; owner = (uint32_t)ow;
+				__threadfence();
+				off = ldv64(&s->rec_off);
+				const uint32_t len1 = ldv32(&s->alloc);             // remote stored length + 1, 0 = unknown
+				clen = len1 ? len1 - 1u : 0xffffffffu;
+			}
+		}
+	}
+	sh->st = st; sh->clen = clen; sh->off = off; sh->owner = owner;
+}
+
+__global__ void __launch_bounds__(GS_THREADS, 1) k_get_small(GetJob job) {
+	extern __shared__ __align__(128) uint8_t smem[];
+	GetShared *sh = reinterpret_cast<GetShared *>(smem);
+	DecodePipe *dp = reinterpret_cast<DecodePipe *>(smem + 128);
+	uint8_t *rec = smem + GS_CTRL;
+	uint8_t *page = rec + gs_recbuf(job.nbytes);
+	const uint32_t i = blockIdx.x, tid = threadIdx.x;
+	const int lane = tid & 31;
+	const unsigned long long u = job.addr[2 * (size_t)i], l = job.addr[2 * (size_t)i + 1];
+	uint8_t *out = job.out + (size_t)i * job.nbytes;
+	const uint32_t s_bar = smem_addr(&sh->bar);
+	if (job.valid && !job.valid[i]) { if (tid == 0) job.status[i] = ST_INVALID; return; }
+	if (tid == 0) {
+		mbar_init(s_bar, 1u);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+	}
+	uint32_t phase = 0;
+	int32_t result = ST_MISS;
+	for (int attempt = 0; attempt < 4; attempt++) {
+		if (tid == 0) gs_lookup(job, u, l, sh);
+		__syncthreads();
+		const int32_t st = sh->st;
+		const uint32_t clen = sh->clen, owner = sh->owner;
+		const unsigned long long off = sh->off;
+		result = st;
+		if (st != ST_HIT && st != ST_REMOTE) break;
+		const uint32_t plen = clen ? clen : job.nbytes;           // payload bytes (raw page when compressed_length is 0)
+		const uint32_t tx = (24u + plen + 15u) & ~15u;
+		const uint8_t *base = job.arena;
+		uint64_t limit = job.arena_size + 256u;                  // every arena is allocated with 256 bytes of slack
+		bool ok = clen <= job.nbytes + 1024u && (off & 15u) == 0;
+		if (st == ST_REMOTE) {
+			base = owner - 1u < GET_MAX_PEERS ? job.peer[owner - 1u] : nullptr;
+			limit = owner - 1u < GET_MAX_PEERS ? job.peer_size[owner - 1u] + 256u : 0;
+			ok = ok && base != nullptr && clen != 0xffffffffu;
+			if (!ok) break;                                      // no path to the owner's arena: REMOTE is the answer
+		}
+		if (!ok || off + tx > limit) { result = ST_MISS; break; }
+		if (st == ST_HIT) {
+			if (tid == 0) { mbar_expect_tx(s_bar, tx); tma_load_1d(smem_addr(rec), base + off, tx, s_bar); }
+			while (!mbar_try_wait(s_bar, phase)) {}
+			phase ^= 1u;
+		} else {
+			// the owner's arena over NVLink: plain 16-byte loads, no local L2 (peer lines are not cached there)
+			const uint4 *src = reinterpret_cast<const uint4 *>(base + off);
+			for (uint32_t k = tid; k < tx / 16u; k += GS_THREADS) reinterpret_cast<uint4 *>(rec)[k] = __ldcg(src + k);
+			__syncthreads();
+		}
+		// the record's own prefix decides (filemap.c:9-12): address and compressed_length
+		const unsigned long long pu = *reinterpret_cast<const unsigned long long *>(rec);
+		const unsigned long long pl = *reinterpret_cast<const unsigned long long *>(rec + 8);
+		const uint32_t pclen = *reinterpret_cast<const uint32_t *>(rec + 16);
+		if (pu != u || pl != l || pclen != clen) {
+			// the slot moved on between the two reads (a put or a compaction on another stream / GPU):
+			// look again; a remote location that no longer holds the record is a miss
+			result = ST_MISS;
+			__syncthreads();
+			if (st == ST_REMOTE) break;
+			continue;
+		}
+		if (clen == 0u) {
+			// raw page (filemap.c:249-251); 8-byte granularity: rec + 24 is not 16-byte aligned
+			for (uint32_t k = tid; k < job.nbytes / 8u; k += GS_THREADS)
+				reinterpret_cast<unsigned long long *>(out)[k] = reinterpret_cast<const unsigned long long *>(rec + 24)[k];
+			__threadfence_system();
+			result = ST_HIT;
+			break;
+		}
+		// three-stage pipeline over the token chain (lz4_decode.cuh): parser, literal copies, match copies
+		if (tid == 0) { dp->parsed = 0; dp->lit_done = 0; dp->mat_done = 0; dp->result = 0; dp->abort = 0; dp->lit_by[0] = dp->lit_by[1] = 0; dp->lit_ended = 0; }
+		__syncthreads();
+		if (tid < 32) lz4_pipe_parse(smem_addr(dp), smem_addr(rec + 24), clen, job.nbytes, lane);
+		else if (tid < 64) lz4_pipe_literals(smem_addr(dp), smem_addr(rec + 24), smem_addr(page), rec + 24, page, 0u, lane);
+		else if (tid < 96) lz4_pipe_matches(smem_addr(dp), smem_addr(page), lane);
+		else lz4_pipe_literals(smem_addr(dp), smem_addr(rec + 24), smem_addr(page), rec + 24, page, 1u, lane);
+		__syncthreads();
+		if (dp->result != (int32_t)clen || dp->abort) { result = ST_BAD_DECODE; break; }     // filemap.c:244-248
+		for (uint32_t k = tid; k < job.nbytes / 16u; k += GS_THREADS)
+			reinterpret_cast<uint4 *>(out)[k] = reinterpret_cast<const uint4 *>(page)[k];
+		__threadfence_system();                           // `out` may be host memory that is read as soon as the status flips
+		result = ST_HIT;
+		break;
+	}
+	// status may live in page-locked host memory that the caller polls: the page first, then the status
+	__syncthreads();
+	if (tid == 0) { __threadfence_system(); *reinterpret_cast<volatile int32_t *>(&job.status[i]) = result; }
+}
+
+int launch_get_small(const GetJob &job, cudaStream_t st) {
+	if (job.n == 0) return 0;
+	const size_t smem = GS_CTRL + gs_recbuf(job.nbytes) + job.nbytes;
+	static size_t configured = 0;
+	if (smem > configured) {
+		CMB_CHECK(cudaFuncSetAttribute(k_get_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		configured = smem;
+	}
+	k_get_small<<<job.n, GS_THREADS, smem, st>>>(job);
+	CMB_CHECK(cudaGetLastError());
+	return 0;
+}
+
+// ------------------------------------------------------------------------------------------
 // fingerprint alone, stream generator, small launchers
 // ------------------------------------------------------------------------------------------
 
@@ -829,7 +957,7 @@ __global__ void k_import_claim(TableView t, const unsigned long long *addr, cons
 	slot_idx[i] = idx;
 }
 __global__ void k_import_apply(TableView t, ArenaView a, const unsigned long long *addr, const uint32_t *owner,
-    const unsigned long long *seq, uint32_t n, const uint32_t *slot_idx) {
+    const unsigned long long *seq, const unsigned long long *loc, uint32_t n, const uint32_t *slot_idx) {
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	uint32_t idx = slot_idx[i];
@@ -842,36 +970,42 @@ __global__ void k_import_apply(TableView t, ArenaView a, const unsigned long lon
 		s.vlen = 0; s.alloc = 0;
 	}
 	if (s.owner == 0) atomicAdd(t.remote, 1ull);
-	s.owner = (unsigned long long)owner[i] + 1;
 	s.addr_u = addr[2 * i]; s.addr_l = addr[2 * i + 1];
+	s.rec_off = loc ? xrec_off(loc[i]) : 0ull; s.alloc = loc ? xrec_len1(loc[i]) : 0u;   // 0 = location unknown
+	__threadfence();
+	s.owner = (unsigned long long)owner[i] + 1;
 }
 int launch_import(TableView t, ArenaView a, const unsigned long long *addr, const uint32_t *owner,
-    const unsigned long long *seq, uint32_t n, uint32_t *slot_idx, cudaStream_t st) {
+    const unsigned long long *seq, const unsigned long long *loc, uint32_t n, uint32_t *slot_idx, cudaStream_t st) {
 	if (n == 0) return 0;
 	k_import_claim<<<GRID1D(n), 0, st>>>(t, addr, seq, n, slot_idx);
 	CMB_CHECK(cudaGetLastError());
-	k_import_apply<<<GRID1D(n), 0, st>>>(t, a, addr, owner, seq, n, slot_idx);
+	k_import_apply<<<GRID1D(n), 0, st>>>(t, a, addr, owner, seq, loc, n, slot_idx);
 	CMB_CHECK(cudaGetLastError());
 	return 0;
 }
 // ---- multi-GPU exchange records, device resident ------------------------------------------------
-// One 32-byte record per chunk of a put step: {u, l, global stream position, owner rank << 32 | stored
-// length}; length < 0 = the chunk stored nothing (edge_fuse_b200/sharding.py has the same layout).
-__global__ void k_pack_records(const unsigned long long *addr, const int32_t *lens, uint32_t n,
-    unsigned long long seq0, unsigned long long stride, uint32_t rank, unsigned long long *out) {
+// One 32-byte record per chunk of a put step: {u, l, global stream position, tail}; tail is
+// xrec_tail(owner rank, arena offset, stored length) (kernels.h; edge_fuse_b200/sharding.py has the
+// same layout).
+__global__ void k_pack_records(const unsigned long long *addr, const int32_t *lens, const unsigned long long *rec_off,
+    uint32_t n, unsigned long long seq0, unsigned long long stride, uint32_t rank, unsigned long long *out) {
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	ulonglong2 a = *reinterpret_cast<const ulonglong2 *>(addr + 2 * (size_t)i);
 	ulonglong2 b;
 	b.x = seq0 + stride * i;
-	b.y = ((unsigned long long)rank << 32) | (uint32_t)lens[i];
+	int32_t len = lens[i];
+	unsigned long long off = (len >= 0 && rec_off) ? rec_off[i] : 0ull;
+	if (off == ~0ull) { len = -1; off = 0; }        // the put was dropped (arena full)
+	b.y = xrec_tail(rank, off, len);
 	reinterpret_cast<ulonglong2 *>(out)[2 * (size_t)i] = a;
 	reinterpret_cast<ulonglong2 *>(out)[2 * (size_t)i + 1] = b;
 }
-int launch_pack_records(const unsigned long long *addr, const int32_t *lens, uint32_t n, unsigned long long seq0,
-    unsigned long long stride, uint32_t rank, unsigned long long *out, cudaStream_t st) {
+int launch_pack_records(const unsigned long long *addr, const int32_t *lens, const unsigned long long *rec_off, uint32_t n,
+    unsigned long long seq0, unsigned long long stride, uint32_t rank, unsigned long long *out, cudaStream_t st) {
 	if (n == 0) return 0;
-	k_pack_records<<<GRID1D(n), 0, st>>>(addr, lens, n, seq0, stride, rank, out);
+	k_pack_records<<<GRID1D(n), 0, st>>>(addr, lens, rec_off, n, seq0, stride, rank, out);
 	CMB_CHECK(cudaGetLastError());
 	return 0;
 }
@@ -882,7 +1016,7 @@ __global__ void k_import_claim_rec(TableView t, const unsigned long long *rec, u
 	if (i >= n) return;
 	const unsigned long long tail = rec[4 * (size_t)i + 3];
 	uint32_t idx = 0xffffffffu;
-	if ((uint32_t)(tail >> 32) != my_rank && (int32_t)(uint32_t)tail >= 0) {
+	if (xrec_owner(tail) != my_rank && xrec_len1(tail) != 0u) {
 		idx = table_find_or_claim(t, fnv_addr(rec[4 * (size_t)i], rec[4 * (size_t)i + 1]));
 		if (idx != 0xffffffffu) atomicMax(&t.slots[idx].seq, rec[4 * (size_t)i + 2]);
 	}
@@ -902,8 +1036,12 @@ __global__ void k_import_apply_rec(TableView t, ArenaView a, const unsigned long
 		s.vlen = 0; s.alloc = 0;
 	}
 	if (s.owner == 0) atomicAdd(t.remote, 1ull);
-	s.owner = (rec[4 * (size_t)i + 3] >> 32) + 1;
+	const unsigned long long tail = rec[4 * (size_t)i + 3];
 	s.addr_u = rec[4 * (size_t)i]; s.addr_l = rec[4 * (size_t)i + 1];
+	// where the record lies in the owner's arena (vlen stays 0: no local record)
+	s.rec_off = xrec_off(tail); s.alloc = xrec_len1(tail);
+	__threadfence();
+	s.owner = (unsigned long long)xrec_owner(tail) + 1;
 }
 int launch_import_records(TableView t, ArenaView a, const unsigned long long *rec, uint32_t n, uint32_t my_rank,
     uint32_t *slot_idx, cudaStream_t st) {

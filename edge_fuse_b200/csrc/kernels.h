@@ -65,6 +65,7 @@ struct EncodeJob {
 	uint8_t *stage;          // n x stage_stride scratch for blocks
 	uint64_t stage_stride;
 	int32_t *lens;           // out: block length, -1 = chunk skipped (superseded inside the batch)
+	unsigned long long *rec_out; // out, optional: arena offset of the stored record per chunk (~0 = dropped)
 	uint64_t *fps;           // out, optional: 2 x u64 per chunk {hi, lo}
 	unsigned int *work;      // dynamic work counter (zeroed by the launcher)
 	uint8_t *gtab;           // group encoder: global position tables, set by the launcher
@@ -96,6 +97,28 @@ struct DecodeJob {
 };
 int launch_decode(const DecodeJob &job, cudaStream_t st);
 
+// Fused small-batch get (one CTA per request): key lookup, record staged in shared memory by TMA,
+// LZ4 decode shared -> shared, page written out with 16-byte stores (device memory or page-locked
+// host memory).  Safe to run on its own stream while puts run on another: records are immutable
+// and the record's own prefix is checked against the request.  peer[r] = base of rank r's arena
+// mapped into this process (NVLink peer memory), for keys whose newest record lives on rank r.
+#define GET_MAX_PEERS 16
+struct GetJob {
+	TableView table;
+	const uint8_t *arena;
+	uint64_t arena_size;
+	const unsigned long long *addr;   // n x {u, l}
+	const uint8_t *valid;             // optional
+	uint32_t n;
+	uint32_t nbytes;                  // page size, <= 65536 for this kernel
+	uint8_t *out;                     // n x nbytes
+	int32_t *status;                  // n
+	const uint8_t *peer[GET_MAX_PEERS];
+	uint64_t peer_size[GET_MAX_PEERS];
+};
+bool get_small_supports(uint32_t nbytes);
+int launch_get_small(const GetJob &job, cudaStream_t st);
+
 int launch_fingerprint(const uint8_t *pages, uint64_t stride, uint32_t nbytes, uint32_t n,
     uint64_t *fps, cudaStream_t st);
 
@@ -109,12 +132,26 @@ int launch_upsert(TableView t, const unsigned long long *addr, const uint8_t *va
 // Multi-GPU index replication: records {addr, owner rank, seq} written on other GPUs.  Newest
 // sequence per key wins; a local record that loses is retired.
 int launch_import(TableView t, ArenaView a, const unsigned long long *addr, const uint32_t *owner,
-    const unsigned long long *seq, uint32_t n, uint32_t *slot_idx, cudaStream_t st);
+    const unsigned long long *seq, const unsigned long long *loc, uint32_t n, uint32_t *slot_idx, cudaStream_t st);
 
 // The same exchange with the records staying on the device: pack one 32-byte record per chunk of a
 // put step, import all-gathered records (rows of my_rank / rows that stored nothing are skipped).
-int launch_pack_records(const unsigned long long *addr, const int32_t *lens, uint32_t n, unsigned long long seq0,
-    unsigned long long stride, uint32_t rank, unsigned long long *out, cudaStream_t st);
+// Record = {u, l, global stream position, tail}; tail = owner rank << 56 | arena offset / 16 << 22 |
+// stored length + 1 (0 = the chunk stored nothing).  The location lets another GPU read the record
+// from the owner's arena over NVLink (k_get_small).
+#define XREC_LEN_BITS 22
+#define XREC_OFF_BITS 34
+__host__ __device__ inline unsigned long long xrec_tail(uint32_t owner, unsigned long long rec_off, int32_t len) {
+	return ((unsigned long long)owner << 56) | (((rec_off >> 4) & ((1ull << XREC_OFF_BITS) - 1)) << XREC_LEN_BITS) |
+	    (unsigned long long)(len < 0 ? 0u : (uint32_t)len + 1u);
+}
+__host__ __device__ inline uint32_t xrec_owner(unsigned long long tail) { return (uint32_t)(tail >> 56); }
+__host__ __device__ inline unsigned long long xrec_off(unsigned long long tail) {
+	return ((tail >> XREC_LEN_BITS) & ((1ull << XREC_OFF_BITS) - 1)) << 4;
+}
+__host__ __device__ inline uint32_t xrec_len1(unsigned long long tail) { return (uint32_t)(tail & ((1u << XREC_LEN_BITS) - 1)); }
+int launch_pack_records(const unsigned long long *addr, const int32_t *lens, const unsigned long long *rec_off, uint32_t n,
+    unsigned long long seq0, unsigned long long stride, uint32_t rank, unsigned long long *out, cudaStream_t st);
 int launch_import_records(TableView t, ArenaView a, const unsigned long long *rec, uint32_t n, uint32_t my_rank,
     uint32_t *slot_idx, cudaStream_t st);
 

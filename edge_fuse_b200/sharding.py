@@ -20,24 +20,41 @@ def shard_positions(rank: int, world: int, n_local: int, base: int = 0) -> np.nd
     return (np.uint64(base) + np.uint64(rank) + np.uint64(world) * np.arange(n_local, dtype=np.uint64))
 
 
-def pack_records(u, l, seq, rank: int, lens) -> np.ndarray:
-    """[n, 4] int64: u, l, seq, (rank << 32 | len & 0xffffffff).  len < 0 marks a chunk that stored
-    nothing (rejected address, superseded inside its batch, dropped) and is ignored by importers."""
+LEN_BITS, OFF_BITS = 22, 34   # word 3: owner rank << 56 | arena offset / 16 << 22 | stored length + 1
+
+
+def pack_records(u, l, seq, rank: int, lens, rec_off=None) -> np.ndarray:
+    """[n, 4] int64: u, l, seq, tail.  tail = rank << 56 | (arena offset / 16) << 22 | (len + 1)
+    (csrc/kernels.h xrec_tail): len < 0 marks a chunk that stored nothing (rejected address,
+    superseded inside its batch, dropped) — its low 22 bits are 0 and importers ignore the row;
+    rec_off = where the record lies in the owner's arena (0 when unknown), for NVLink reads."""
     n = len(u)
     rec = np.empty((n, REC_WORDS), dtype=np.int64)
     rec[:, 0] = np.asarray(u, dtype=np.uint64).view(np.int64)
     rec[:, 1] = np.asarray(l, dtype=np.uint64).view(np.int64)
     rec[:, 2] = np.asarray(seq, dtype=np.uint64).view(np.int64)
-    rec[:, 3] = (np.int64(rank) << np.int64(32)) | (np.asarray(lens, dtype=np.int64) & np.int64(0xFFFFFFFF))
+    ln = np.asarray(lens, dtype=np.int64)
+    len1 = np.where(ln < 0, 0, ln + 1).astype(np.uint64)
+    off = np.zeros(n, dtype=np.uint64) if rec_off is None else np.asarray(rec_off, dtype=np.uint64)
+    off = np.where(ln < 0, np.uint64(0), off)
+    tail = (np.uint64(rank) << np.uint64(56)) | (((off >> np.uint64(4)) & np.uint64((1 << OFF_BITS) - 1)) << np.uint64(LEN_BITS)) | len1
+    rec[:, 3] = tail.view(np.int64)
     return rec
 
 
 def unpack_records(rec):
-    """-> u, l, seq, owner, length (arrays; works on numpy arrays and torch tensors alike)."""
+    """-> u, l, seq, owner, length (arrays; works on numpy arrays and torch tensors alike);
+    length = -1 for rows that stored nothing."""
     u, l, seq, tail = rec[..., 0], rec[..., 1], rec[..., 2], rec[..., 3]
-    owner = tail >> 32
-    length = ((tail & 0xFFFFFFFF) ^ 0x80000000) - 0x80000000      # sign-extend the low 32 bits
+    owner = (tail >> 56) & 0xFF
+    length = (tail & ((1 << LEN_BITS) - 1)) - 1
     return u, l, seq, owner, length
+
+
+def unpack_locations(rec):
+    """-> arena offset of each row's record in its owner's arena (bytes)."""
+    tail = rec[..., 3]
+    return ((tail >> LEN_BITS) & ((1 << OFF_BITS) - 1)) << 4
 
 
 def all_gather_records(rec_tensor, group=None):
@@ -86,16 +103,37 @@ def import_gathered(engine, gathered, rank: int) -> int:
         return 0
     addr = rows[:, :2].contiguous()
     seq = rows[:, 2].contiguous()
-    owner = (rows[:, 3] >> 32).to(torch.int32).contiguous()
+    loc = rows[:, 3].contiguous()
+    owner = ((rows[:, 3] >> 56) & 0xFF).to(torch.int32).contiguous()
     if rows.is_cuda:
         torch.cuda.current_stream(rows.device).synchronize()
         from .binding import lib, _check
-        _check(lib().cmb200_import_remote(engine.h, n, addr.data_ptr(), owner.data_ptr(), seq.data_ptr(), 1),
+        _check(lib().cmb200_import_remote(engine.h, n, addr.data_ptr(), owner.data_ptr(), seq.data_ptr(), loc.data_ptr(), 1),
                "cmb200_import_remote")
     else:
         a = addr.numpy().view(np.uint64)
-        engine.import_remote(a[:, 0], a[:, 1], owner.numpy().view(np.uint32), seq.numpy().view(np.uint64))
+        engine.import_remote(a[:, 0], a[:, 1], owner.numpy().view(np.uint32), seq.numpy().view(np.uint64),
+                             loc.numpy().view(np.uint64))
     return n
+
+
+def open_peers(engine, rank: int, world: int, group=None) -> None:
+    """Maps every other rank's arena into this process (CUDA IPC -> NVLink peer memory) so that
+    cmb200_get_small serves keys whose newest record lives on another GPU.  One all-gather of the
+    64-byte IPC handles; ranks must be processes on one box."""
+    import torch
+    import torch.distributed as dist
+    handle, size = engine.arena_ipc_handle()
+    mine = torch.tensor(list(handle) + list(int(size).to_bytes(8, "little")), dtype=torch.uint8)
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    mine = mine.to(dev)
+    allh = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allh, mine, group=group)
+    for r in range(world):
+        if r == rank:
+            continue
+        raw = bytes(allh[r].cpu().tolist())
+        engine.open_peer(r, raw[:64], int.from_bytes(raw[64:72], "little"))
 
 
 class StepExchange:
@@ -185,7 +223,7 @@ class StepExchange:
         k = (self.count - 1) & 1
         self.torch.cuda.synchronize(self.dev)
         tail = self.rec[k][:, 3].cpu().numpy()
-        return (((tail & 0xFFFFFFFF) ^ 0x80000000) - 0x80000000).astype(np.int64)
+        return ((tail & ((1 << LEN_BITS) - 1)) - 1).astype(np.int64)
 
     def breakdown_ms(self) -> dict:
         """Mean device time of the exchange stages (needs timing=True and a synchronized device)."""

@@ -163,8 +163,32 @@ int cmb200_load(cmb200_engine *e, const char *path, uint64_t *records_out);
  * others' records: per key the highest sequence wins, exactly as sequential puts would resolve
  * (SURVEY.md §8e "ordering caveat"); a local record that loses is retired. */
 int cmb200_set_stream_order(cmb200_engine *e, uint64_t next_seq, uint64_t stride);
+/* loc[i] (optional) = word 3 of the exchange record of row i: owner rank << 56 | arena offset / 16
+ * << 22 | stored length + 1 — where the record lies in the owner's arena, so that cmb200_get_small
+ * can read it over NVLink once cmb200_open_peer has mapped that arena. */
 int cmb200_import_remote(cmb200_engine *e, size_t n, const cmb200_addr *addr, const uint32_t *owner,
-    const uint64_t *seq, int arrays_on_device);
+    const uint64_t *seq, const uint64_t *loc, int arrays_on_device);
+/* The other ranks' arenas as NVLink peer memory.  Every rank exports the CUDA IPC handle of its
+ * arena (64 bytes; exchange them with one all-gather), and opens the handles of the ranks it wants
+ * to read from.  A cmb200_get_small of a key whose newest record lives on rank r then copies the
+ * record straight out of rank r's arena (the location travelled with the exchange record) and
+ * decodes it locally: replaces cachemap_get's LMDB read (cachemap.c:168-184, filemap.c:217-262) on
+ * a box-global index.  Without a mapped peer such a get reports CMB200_REMOTE.  A location that no
+ * longer holds the record (the owner compacted its arena since the exchange) is a miss. */
+int cmb200_arena_ipc_handle(cmb200_engine *e, void *handle64_out, uint64_t *arena_bytes_out);
+int cmb200_open_peer(cmb200_engine *e, uint32_t rank, const void *handle64, uint64_t arena_bytes);
+
+/* Small batches of gets (cachemap_get from FUSE worker threads, n <= a few hundred): ONE fused
+ * kernel per call — key lookup, record staged in shared memory by TMA, LZ4 decode shared -> shared,
+ * page written with 16-byte stores — on a stream and a lock of its own, so a get neither waits for
+ * a put batch in flight nor copies its result a second time: pages_out must be page-locked host
+ * memory (cmb200_host_alloc; the kernel writes it directly) or device memory.  Records are
+ * immutable and every rewrite goes to fresh arena space, so a get that overlaps a put of the same
+ * key returns the old or the new page, never a mix (the reference's LMDB snapshot reads,
+ * filemap.c:223-231).  Page sizes above 64 KiB are not served by this call (-2): use
+ * cmb200_get_batch.  status_out as cmb200_get_batch. */
+int cmb200_get_small(cmb200_engine *e, size_t n, const cmb200_addr *addr, void *pages_out, int32_t *status_out);
+
 /* Lookup only: status_out[i] in CMB200_{MISS,HIT,BAD_ENTRY,REMOTE}; owner_out[i] = owning rank for
  * CMB200_REMOTE. */
 int cmb200_locate_batch(cmb200_engine *e, size_t n, const cmb200_addr *addr, int32_t *status_out,

@@ -74,8 +74,13 @@ def test_two_rank_exchange():
 def test_pack_unpack_roundtrip():
     u = np.array([2**63 + 5, 1], dtype=np.uint64)
     l = np.array([7, 2**44 - 1], dtype=np.uint64)
-    rec = sharding.pack_records(u, l, np.array([9, 2**40], dtype=np.uint64), 3, np.array([-1, 65794]))
+    rec = sharding.pack_records(u, l, np.array([9, 2**40], dtype=np.uint64), 3, np.array([-1, 65794]),
+                                rec_off=np.array([4096, 179 * 2**30 + 48], dtype=np.uint64))
     uu, ll, ss, oo, nn = sharding.unpack_records(rec)
     assert (np.uint64(uu) == u).all() and (np.uint64(ll) == l).all()
     assert oo.tolist() == [3, 3] and nn.tolist() == [-1, 65794] and np.uint64(ss).tolist() == [9, 2**40]
+    # the location travels with rows that stored something (16-byte units, 34 bits: arenas up to 256 GiB)
+    assert sharding.unpack_locations(rec).tolist() == [0, 179 * 2**30 + 48]
+    rec7 = sharding.pack_records(u, l, np.array([1, 2], dtype=np.uint64), 7, np.array([0, 2**21]))
+    assert sharding.unpack_records(rec7)[3].tolist() == [7, 7] and sharding.unpack_records(rec7)[4].tolist() == [0, 2**21]
     assert (sharding.shard_positions(1, 4, 3, 10) == np.array([11, 15, 19], dtype=np.uint64)).all()

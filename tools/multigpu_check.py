@@ -1,5 +1,7 @@
 #!/usr/bin/env python
-"""2+ GPU functional check of the sharded put path (run under torchrun on the GPU box):
+"""2+ GPU functional check of the sharded put path and the cross-GPU read path (run under torchrun on
+the GPU box; e.g. gpurun --gpus 2 -- python -m torch.distributed.run --nproc-per-node 2 --master-addr
+127.0.0.1 tools/multigpu_check.py):
 every rank puts its round-robin shard of a stream with 30 % same-address repeats, the ranks
 exchange key records, and afterwards every rank's index must agree with a sequential pass:
 the newest writer of each key is HIT on its owner and REMOTE(owner) everywhere else.
@@ -66,7 +68,21 @@ for mode in ("host", "device"):
     tot = torch.tensor([st["entries"]], device="cuda")
     dist.all_reduce(tot)
     ok = ok and int(tot.item()) == distinct and st["entries"] + st["remote_entries"] == distinct
-    print(f"rank {rank} [{mode} exchange]: ok={bool(ok)} local={st['entries']} remote={st['remote_entries']} distinct={distinct}", flush=True)
+    remote_ok = None
+    if mode == "device":
+        # cross-GPU read path: map the other ranks' arenas (CUDA IPC -> NVLink peer memory); a get of a key
+        # whose newest record lives elsewhere then reads that record out of its owner's arena and decodes it here
+        sharding.open_peers(eng, rank, world)
+        dist.barrier()
+        pick = np.arange(0, len(qc), max(1, len(qc) // 1024))[:1024]
+        out, gst = eng.get_small(qn[pick], (qo >> np.uint64(16))[pick])
+        want = np.stack([E.gen_chunk_host(42, int(c), bs) for c in qc[pick]])
+        remote_ok = bool((gst == E.HIT).all() and (out == want).all())
+        n_remote = int((exp_owner[pick] != rank).sum())
+        ok = ok and remote_ok and n_remote > 0
+        dist.barrier()                                  # nobody closes its arena while a peer still reads it
+    print(f"rank {rank} [{mode} exchange]: ok={bool(ok)} local={st['entries']} remote={st['remote_entries']} distinct={distinct}"
+          + (f" remote_gets_ok={remote_ok}" if remote_ok is not None else ""), flush=True)
     all_ok = all_ok and bool(ok)
     eng.dev_free(d)
     eng.close()
