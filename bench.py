@@ -344,7 +344,7 @@ def run_config_2_3(args, E, O, torch, local, d_pages, h_ptr, h_pages, peak, thre
     return c2, c3
 
 
-def run_config_4(args, E, O, torch, dist, rank, world, local, d_pages, threads):
+def run_config_4(args, E, O, torch, dist, rank, world, local, d_pages, threads, h_ptr=None, h_pages=None):
     """N > 1: a stream with 30 % same-address duplicates sharded round-robin, so that the same key is
     written by different ranks inside one step; afterwards every rank's index replica must equal the
     outcome of a sequential pass over the global stream (SURVEY.md App. B rule 4)."""
@@ -390,6 +390,27 @@ def run_config_4(args, E, O, torch, dist, rank, world, local, d_pages, threads):
     own = np.nonzero(exp_owner == rank)[0][: args.parity_chunks // 8]
     par = parity_gate(O, eng, O.gen_chunks(SEED + 1, qc[own], CHUNK, max(1, threads // world)), qn[own],
                       (qo >> np.uint64(PSHIFT))[own], None, max(1, threads // world))
+    # cross-GPU read path: keys whose newest record lives on another rank are read out of the owner's
+    # arena over NVLink (CUDA IPC peer mapping) and decoded here
+    remote = {"served": False}
+    if h_ptr is not None:
+        sharding.open_peers(eng, rank, world)
+        dist.barrier()
+        theirs = np.nonzero(exp_owner != rank)[0]
+        pick = theirs[np.linspace(0, len(theirs) - 1, min(len(theirs), 2048)).astype(np.int64)]
+        qp = (qo >> np.uint64(PSHIFT))[pick]
+        eng.get_small(qn[pick[:64]], qp[:64], out=h_ptr)                        # warm-up
+        t0 = time.perf_counter()
+        _, gst = eng.get_small(qn[pick], qp, out=h_ptr)
+        dt = time.perf_counter() - t0
+        want = O.gen_chunks(SEED + 1, qc[pick], CHUNK, max(1, threads // world))
+        good = bool((gst == E.HIT).all() and (h_pages.reshape(-1, CHUNK)[: len(pick)] == want).all())
+        ok = ok and good
+        remote = {"served": good, "gets": int(len(pick)), "gibs_per_rank": len(pick) * CHUNK / GIB / dt,
+                  "path": "cmb200_get_small: record copied from the owner's arena over NVLink (peer memory), LZ4 decode on the "
+                          "requesting GPU, page written to page-locked host memory"}
+        eng.close_peers()
+        dist.barrier()                                      # nobody frees its arena while a peer still maps it
     t = torch.tensor([int(ok), st["entries"], par["mismatches"], ms], dtype=torch.float64, device="cuda")
     tmin, tsum, tmax = t.clone(), t.clone(), t.clone()
     dist.all_reduce(tmin, op=dist.ReduceOp.MIN); dist.all_reduce(tsum); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -400,8 +421,9 @@ def run_config_4(args, E, O, torch, dist, rank, world, local, d_pages, threads):
            "put_gibs": n_tot * CHUNK / GIB / (float(tmax[3].item()) * 1e-3), "distinct": distinct,
            "entries_sum_over_ranks": int(tsum[1].item()), "index_matches_sequential": all_ok,
            "parity_mismatches": int(tsum[2].item()), "parity_chunks_per_rank": par["chunks"],
+           "remote_gets_rank0": remote,
            "gate": "every key HIT on the rank of its last writer and REMOTE(owner) elsewhere; sum of entries == distinct; "
-                   "owned records == oracle"}
+                   "owned records == oracle; pages fetched from other ranks' arenas == generator"}
     assert all_ok, f"config 4: index replica differs from the sequential model on rank {rank}: {res}"
     return res
 
@@ -623,7 +645,7 @@ def run_ours(args):
         if world == 1:
             configs["C2"], configs["C3"] = run_config_2_3(args, E, O, torch, local, d_pages, h_ptr, h_pages, peak, host_threads)
         else:
-            configs["C4"] = run_config_4(args, E, O, torch, dist, rank, world, local, d_pages, host_threads)
+            configs["C4"] = run_config_4(args, E, O, torch, dist, rank, world, local, d_pages, host_threads, h_ptr, h_pages)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

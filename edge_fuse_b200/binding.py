@@ -32,7 +32,7 @@ EXPORTED_SYMBOLS = [
     "cmb200_read_fingerprints", "cmb200_get_stats", "cmb200_compose_keys",
     "cmb200_set_stream_order", "cmb200_import_remote", "cmb200_locate_batch", "cmb200_save", "cmb200_load",
     "cmb200_put_step", "cmb200_import_records_dev", "cmb200_compact",
-    "cmb200_get_small", "cmb200_arena_ipc_handle", "cmb200_open_peer",
+    "cmb200_get_small", "cmb200_arena_ipc_handle", "cmb200_open_peer", "cmb200_close_peers",
     "cmb200_lz4_encode_batch", "cmb200_lz4_decode_batch", "cmb200_fingerprint_batch", "cmb200_fingerprint_dev",
     "cmb200_gen_chunk_host", "cmb200_gen_chunks_dev", "cmb200_gen_stream_ids", "cmb200_gen_addr",
 ]
@@ -126,6 +126,7 @@ def lib() -> C.CDLL:
         "cmb200_get_small": (i32, [vp, sz, vp, vp, vp]),
         "cmb200_arena_ipc_handle": (i32, [vp, vp, vp]),
         "cmb200_open_peer": (i32, [vp, C.c_uint32, vp, C.c_uint64]),
+        "cmb200_close_peers": (i32, [vp]),
         "cmb200_locate_batch": (i32, [vp, sz, vp, vp, vp]),
         "cmb200_compose_keys": (i32, [i32, sz, vp, vp, vp, i32, vp, vp, vp]),
         "cmb200_lz4_encode_batch": (i32, [i32, vp, sz, u32, sz, i32, vp, sz, vp, vp]),
@@ -362,6 +363,9 @@ class Engine:
     def open_peer(self, rank: int, handle: bytes, arena_bytes: int):
         buf = (C.c_uint8 * 64).from_buffer_copy(handle)
         _check(lib().cmb200_open_peer(self.h, rank, buf, arena_bytes), "cmb200_open_peer")
+
+    def close_peers(self):
+        _check(lib().cmb200_close_peers(self.h), "cmb200_close_peers")
 
     def unset(self, u, l):
         addr = _addr_array(u, l)

@@ -714,6 +714,17 @@ extern "C" int cmb200_get_small(cmb200_engine *e, size_t n, const cmb200_addr *a
 
 // ---- peers: the other ranks' arenas, mapped for NVLink reads -------------------------------------
 
+extern "C" int cmb200_close_peers(cmb200_engine *e) {
+	std::lock_guard<std::mutex> g(e->get_mu);
+	CMB_CHECK(cudaSetDevice(e->device));
+	CMB_CHECK(cudaStreamSynchronize(e->gst));
+	for (int r = 0; r < GET_MAX_PEERS; r++) {
+		if (e->peer_base[r]) cudaIpcCloseMemHandle((void *)e->peer_base[r]);
+		e->peer_base[r] = nullptr; e->peer_size[r] = 0;
+	}
+	return 0;
+}
+
 extern "C" int cmb200_arena_ipc_handle(cmb200_engine *e, void *handle64, uint64_t *arena_bytes_out) {
 	CMB_CHECK(cudaSetDevice(e->device));
 	cudaIpcMemHandle_t h;

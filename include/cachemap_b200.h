@@ -177,6 +177,9 @@ int cmb200_import_remote(cmb200_engine *e, size_t n, const cmb200_addr *addr, co
  * longer holds the record (the owner compacted its arena since the exchange) is a miss. */
 int cmb200_arena_ipc_handle(cmb200_engine *e, void *handle64_out, uint64_t *arena_bytes_out);
 int cmb200_open_peer(cmb200_engine *e, uint32_t rank, const void *handle64, uint64_t arena_bytes);
+/* Unmaps every peer arena (call on all ranks, then synchronise the ranks, before any of them
+ * destroys its engine: an arena must not be freed while another process still maps it). */
+int cmb200_close_peers(cmb200_engine *e);
 
 /* Small batches of gets (cachemap_get from FUSE worker threads, n <= a few hundred): ONE fused
  * kernel per call — key lookup, record staged in shared memory by TMA, LZ4 decode shared -> shared,

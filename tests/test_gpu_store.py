@@ -927,3 +927,52 @@ def test_reference_exerciser_hit_ratios(E, gpu, tmp_path):
     print("exerciser hit ratios % (ours, reference):", report)
     for phase, (a, b) in report.items():
         assert abs(a - b) <= 2.0, report
+
+
+@pytest.mark.gpu
+def test_cache_directory_interchange_with_the_reference(E, gpu, oracle, tmp_path):
+    """a cache directory written by one implementation is readable by the other,
+    through tools/snap2lmdb (test infrastructure that links the compiled reference; LMDB stays out of
+    the product).  (1) pages put through the GPU path -> snapshot -> LMDB files -> the reference's
+    cachemap_get returns them; (2) pages put through the reference -> LMDB files -> snapshot -> this
+    library restores them on first use and cachemap_get returns them."""
+    import ctypes as C
+    import subprocess
+    import sys
+    R = oracle.ref()
+    if R is None:
+        pytest.skip("oracle/_ref was not built")
+    sys.path.insert(0, os.path.dirname(__file__))
+    from test_oracle_pin import _build_snap2lmdb
+    exe = _build_snap2lmdb(tmp_path)
+    n = 48
+    pages = np.stack([datagen.make_page("RTZMPAX"[i % 7], 65536, 300 + i) for i in range(n)])
+    off = np.arange(n, dtype=np.uint64) << np.uint64(16)
+    nh = np.full(n, 4242, dtype=np.uint64)
+    gen = np.full(n, 5, dtype=np.uint32)
+    # (1) GPU -> reference
+    d_gpu, d_lmdb = tmp_path / "gpu", tmp_path / "lmdb"
+    d_gpu.mkdir(); d_lmdb.mkdir()
+    cm = E.Cachemap(str(d_gpu), 2048, 12, 16)
+    cm.put_batch(off, nh, gen, pages)
+    assert cm.checkpoint() == 0
+    cm.free()
+    snap = str(d_gpu / "cachemap_b200.snap")
+    out = subprocess.run([exe, "to-lmdb", snap, str(d_lmdb), "2048", "16"], capture_output=True, text=True)
+    assert out.returncode == 0 and f"{n} of {n}" in out.stdout, out.stdout + out.stderr
+    rcm = R.cachemap_create(str(d_lmdb).encode(), 2048, 12, 16)
+    for i in range(n):
+        p = R.cachemap_get(rcm, int(off[i]), 4242, 5)
+        assert p and bytes((C.c_uint8 * 65536).from_address(p)) == pages[i].tobytes(), i
+    # (2) reference -> GPU
+    d_ref, d_back = tmp_path / "ref", tmp_path / "back"
+    d_ref.mkdir(); d_back.mkdir()
+    rcm2 = R.cachemap_create(str(d_ref).encode(), 2048, 12, 16)
+    for i in range(n):
+        R.cachemap_put(rcm2, int(off[i]), 99, 7, pages[n - 1 - i].ctypes.data)
+    out = subprocess.run([exe, "from-lmdb", str(d_ref), str(d_back / "cachemap_b200.snap"), "16"], capture_output=True, text=True)
+    assert out.returncode == 0 and f"{n} records" in out.stdout, out.stdout + out.stderr
+    cm2 = E.Cachemap(str(d_back), 2048, 12, 16)
+    got, hit = cm2.get_batch(off, np.full(n, 99, dtype=np.uint64), np.full(n, 7, dtype=np.uint32))
+    assert hit.all() and (got == pages[::-1]).all()
+    cm2.free()

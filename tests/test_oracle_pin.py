@@ -166,3 +166,48 @@ def test_parity_gate_detects_a_wrong_record(oracle):
     l2 = lens.copy(); l2[0] -= 1
     assert oracle.parity_records(pages, u, l, recs, l2, threads=1)["mismatches"] == 1
     assert oracle.parity_records(pages, u + np.uint64(1), l, recs, lens, threads=2)["mismatches"] == 12
+
+
+def _build_snap2lmdb(tmp_path):
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref_dir, ora_dir = os.path.join(root, "oracle", "_ref"), os.path.join(root, "oracle")
+    exe = str(tmp_path / "snap2lmdb")
+    subprocess.check_call(["gcc", "-O2", "-I", os.path.join(root, "include"), os.path.join(root, "tools", "snap2lmdb.c"), "-o", exe,
+                           "-L", ref_dir, "-L", ora_dir, "-l:libcachemap_ref.so", "-l:liboracle.so",
+                           f"-Wl,-rpath,{ref_dir}", f"-Wl,-rpath,{ora_dir}", "-lpthread"])
+    return exe
+
+
+def test_snapshot_lmdb_interchange_on_the_reference_side(oracle, tmp_path):
+    """tools/snap2lmdb (test infrastructure linking the compiled reference): an LMDB cache directory
+    written by the reference becomes a snapshot file in this library's format and back; the
+    reference reads every page again, and the snapshot parses with the independent reader."""
+    import ctypes as C
+    import subprocess
+    import numpy as np
+    from oracle import snapshot as S
+    R = oracle.ref()
+    if R is None:
+        import pytest
+        pytest.skip("oracle/_ref was not built")
+    exe = _build_snap2lmdb(tmp_path)
+    pages = oracle.gen_chunks(42, np.arange(24, dtype=np.uint64), 65536, 2)
+    a, b = tmp_path / "lmdb_a", tmp_path / "lmdb_b"
+    a.mkdir(); b.mkdir()
+    cm = R.cachemap_create(str(a).encode(), 2048, 12, 16)
+    for i in range(24):
+        R.cachemap_put(cm, i << 16, 777, 3, pages[i].ctypes.data)
+    snap = str(tmp_path / "cachemap_b200.snap")
+    assert "24 records" in subprocess.run([exe, "from-lmdb", str(a), snap, "16"], capture_output=True, text=True, check=True).stdout
+    pshift, flags, recs = S.read_snapshot(snap)
+    assert pshift == 16 and flags == 0 and len(recs) == 24 and all(ts > 0 for ts, _, _, _ in recs)
+    want = {oracle.record_prefix(777, (3 << 44) | i, len(oracle.lz4_encode(pages[i])))[:20] + oracle.lz4_encode(pages[i]) for i in range(24)}
+    got = {bytes(rec[:20]) + bytes(rec[24:]) for _, _, _, rec in recs}          # the 4 pad bytes are unspecified in the reference
+    assert got == want
+    out = subprocess.run([exe, "to-lmdb", snap, str(b), "2048", "16"], capture_output=True, text=True, check=True).stdout
+    assert "24 of 24" in out
+    cm2 = R.cachemap_create(str(b).encode(), 2048, 12, 16)
+    for i in range(24):
+        p = R.cachemap_get(cm2, i << 16, 777, 3)
+        assert p and bytes((C.c_uint8 * 65536).from_address(p)) == pages[i].tobytes()

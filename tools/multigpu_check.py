@@ -80,7 +80,8 @@ for mode in ("host", "device"):
         remote_ok = bool((gst == E.HIT).all() and (out == want).all())
         n_remote = int((exp_owner[pick] != rank).sum())
         ok = ok and remote_ok and n_remote > 0
-        dist.barrier()                                  # nobody closes its arena while a peer still reads it
+        eng.close_peers()
+        dist.barrier()                                  # nobody frees its arena while a peer still maps it
     print(f"rank {rank} [{mode} exchange]: ok={bool(ok)} local={st['entries']} remote={st['remote_entries']} distinct={distinct}"
           + (f" remote_gets_ok={remote_ok}" if remote_ok is not None else ""), flush=True)
     all_ok = all_ok and bool(ok)
