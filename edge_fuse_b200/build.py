@@ -38,6 +38,16 @@ def _newer(src_paths, target) -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """CMB200_NVCC_EXTRA (e.g. "-DCMB_OUT_HINT=1") adds compile flags and CMB200_BUILD_OUT names the
+    output file: a differently tuned build of the same library next to the default one, loaded by
+    setting CMB200_LIB (tuning experiments; the default build takes neither)."""
+    global LIB, OBJ
+    extra = os.environ.get("CMB200_NVCC_EXTRA", "").split()
+    out = os.environ.get("CMB200_BUILD_OUT")
+    if out:
+        LIB = os.path.join(HERE, out)
+        OBJ = os.path.join(HERE, "build_" + out.replace(".", "_"))
+        force = True
     os.makedirs(OBJ, exist_ok=True)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
     deps += [os.path.join(HERE, "..", "include", f) for f in os.listdir(os.path.join(HERE, "..", "include"))]
@@ -47,7 +57,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objs = []
     for src in CU_SOURCES:
         obj = os.path.join(OBJ, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         subprocess.run(cmd, check=True)
@@ -59,10 +69,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
         objs.append(obj)
     subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs,
                     "-Xlinker", "-soname=libcachemap.so.0.0", "-lpthread"], check=True)
-    link = os.path.join(HERE, "libcachemap.so")
-    if os.path.lexists(link):
-        os.remove(link)
-    os.symlink("libcachemap.so.0.0", link)
+    if not out:
+        link = os.path.join(HERE, "libcachemap.so")
+        if os.path.lexists(link):
+            os.remove(link)
+        os.symlink("libcachemap.so.0.0", link)
     return LIB
 
 

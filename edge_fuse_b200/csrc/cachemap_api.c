@@ -33,6 +33,7 @@
 #include "../../include/cachemap_b200.h"
 
 #define COMBINE_MAX 256         /* get/unset requests one leader takes per GPU batch */
+#define LEADERS 2               /* batches of gets that may be in flight at once (each on its own engine lane) */
 #define FLUSH_MAX 1024          /* pages the flusher hands over per GPU batch */
 #define PNUM_SHIFT 44           /* cachemap.c:155 */
 
@@ -68,14 +69,14 @@ struct filemap {
 	pthread_mutex_t init_mu;
 	int init_state;         /* 0 = not yet, 1 = ready, -1 = failed */
 	cmb200_engine *eng;
-	uint8_t *h_stage;       /* page-locked, 2 x COMBINE_MAX pages (get results, two batches alternate) */
-	int stage_turn;         /* stage buffer of the next batch (leader only) */
-	int stage_readers[2];   /* waiters still copying their page out of each buffer (under q_mu) */
+	uint8_t *h_stage;       /* page-locked, LEADERS x 2 x COMBINE_MAX pages (get results; two buffers alternate per leader slot) */
+	int stage_turn[LEADERS];        /* stage buffer of the slot's next batch */
+	int stage_readers[2 * LEADERS]; /* waiters still copying their page out of each buffer (under q_mu) */
+	int leader_busy[LEADERS];       /* a batch is being run in this slot (under q_mu) */
 	/* combining queue (gets, unsets) */
 	pthread_mutex_t q_mu;
 	pthread_cond_t q_cv;
 	struct fm_req *q_head, *q_tail;
-	int leader_active;
 	/* write-behind ring: slots [wb_tail, wb_head) are in use, numbered modulo wb_n */
 	pthread_mutex_t wb_mu;
 	pthread_cond_t wb_space, wb_work, wb_idle;
@@ -127,7 +128,7 @@ filemap_engine_ready(struct filemap *m)
 		cfg.flags = env_long("CMB200_FINGERPRINT", 0) ? CMB200_FINGERPRINT : 0;
 		m->eng = cmb200_engine_create(&cfg);
 		if (m->eng) {
-			m->h_stage = cmb200_host_alloc((size_t)2 * COMBINE_MAX * m->bsize);
+			m->h_stage = cmb200_host_alloc((size_t)2 * LEADERS * COMBINE_MAX * m->bsize);
 			/* ring of ~64 MiB by default, at least 64 pages */
 			long slots = env_long("CMB200_WB_SLOTS", (64L << 20) / m->bsize);
 			if (slots > 0 && slots < 64)
@@ -475,9 +476,9 @@ filemap_ring_lookup(struct filemap *m, const cmb200_addr *addr, void *dst)
 	return page;
 }
 
-/* Runs one combined batch of gets / unsets.  Called by the leader without q_mu held. */
+/* Runs one combined batch of gets / unsets in leader slot `ls`.  Called by the leader without q_mu held. */
 static void
-filemap_run_batch(struct filemap *m, struct fm_req **reqs, int count)
+filemap_run_batch(struct filemap *m, struct fm_req **reqs, int count, int ls)
 {
 	cmb200_addr addr[COMBINE_MAX];
 	int32_t status[COMBINE_MAX];
@@ -504,8 +505,8 @@ filemap_run_batch(struct filemap *m, struct fm_req **reqs, int count)
 	 * The hits are NOT copied here: every waiter copies its own page out of the stage when it wakes
 	 * up (filemap_submit_many), so a batch of k pages costs the leader no k memcpys; the two stage
 	 * buffers alternate, and a buffer is reused only when its waiters are done with it. */
-	const int sb = m->stage_turn;
-	m->stage_turn ^= 1;
+	const int sb = 2 * ls + m->stage_turn[ls];
+	m->stage_turn[ls] ^= 1;
 	uint8_t *stage = m->h_stage + (size_t)sb * COMBINE_MAX * (size_t)m->bsize;
 	if (k) {
 		pthread_mutex_lock(&m->q_mu);
@@ -536,7 +537,7 @@ filemap_run_batch(struct filemap *m, struct fm_req **reqs, int count)
 static void
 filemap_copy_out(struct filemap *m, struct fm_req *reqs, int count)
 {
-	int released[2] = { 0, 0 };
+	int released[2 * LEADERS] = { 0 }, any = 0;
 	for (int i = 0; i < count; i++) {
 		struct fm_req *r = &reqs[i];
 		if (!r->staged)
@@ -545,12 +546,13 @@ filemap_copy_out(struct filemap *m, struct fm_req *reqs, int count)
 		if (r->out)
 			memcpy(r->out, r->staged, (size_t)m->bsize);
 		released[r->stage_buf]++;
+		any = 1;
 		r->staged = NULL;
 	}
-	if (released[0] || released[1]) {
+	if (any) {
 		pthread_mutex_lock(&m->q_mu);
-		m->stage_readers[0] -= released[0];
-		m->stage_readers[1] -= released[1];
+		for (int b = 0; b < 2 * LEADERS; b++)
+			m->stage_readers[b] -= released[b];
 		pthread_cond_broadcast(&m->q_cv);
 		pthread_mutex_unlock(&m->q_mu);
 	}
@@ -572,13 +574,19 @@ filemap_submit_many(struct filemap *m, struct fm_req *reqs, int count)
 		m->q_head = &reqs[0];
 	m->q_tail = req;
 	while (!req->done) {
-		if (m->leader_active) {
+		/* Up to LEADERS batches are in flight at once: while one batch's kernel runs, the callers that
+		 * arrived meanwhile form the next one instead of waiting for it.  Unsets stay alone (they
+		 * change the table the gets read by key). */
+		int ls = -1;
+		for (int k = 0; k < LEADERS; k++)
+			if (!m->leader_busy[k]) { ls = k; break; }
+		if (ls < 0 || !m->q_head) {
 			pthread_cond_wait(&m->q_cv, &m->q_mu);
 			continue;
 		}
 		struct fm_req *batch[COMBINE_MAX];
 		int nb = 0;
-		m->leader_active = 1;
+		m->leader_busy[ls] = 1;
 		while (m->q_head && nb < COMBINE_MAX) {
 			batch[nb++] = m->q_head;
 			m->q_head = m->q_head->next;
@@ -589,14 +597,14 @@ filemap_submit_many(struct filemap *m, struct fm_req *reqs, int count)
 		/* a long request chain spans several batches: take my pages of the earlier ones out first,
 		 * the batch I am about to run may need their stage buffer */
 		filemap_copy_out(m, reqs, count);
-		filemap_run_batch(m, batch, nb);
+		filemap_run_batch(m, batch, nb, ls);
 		pthread_mutex_lock(&m->q_mu);
 		for (int i = 0; i < nb; i++) {
 			if (batch[i]->staged)
 				m->stage_readers[batch[i]->stage_buf]++;
 			batch[i]->done = 1;
 		}
-		m->leader_active = 0;
+		m->leader_busy[ls] = 0;
 		pthread_cond_broadcast(&m->q_cv);
 	}
 	pthread_mutex_unlock(&m->q_mu);

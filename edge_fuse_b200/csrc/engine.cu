@@ -9,7 +9,9 @@
 // commit + table publish), sub-batch k+1's copy overlapping sub-batch k's kernels.
 // A get batch is: k_lookup -> k_decode -> D2H copy.
 #include <algorithm>
+#include <atomic>
 #include <mutex>
+#include <shared_mutex>
 #include <string>
 #include <new>
 #include <stdio.h>
@@ -42,15 +44,19 @@ struct cmb200_engine {
 	cudaStream_t st = nullptr, copy = nullptr;
 	// small gets (cmb200_get_small) have their own stream, lock and buffers: they neither queue behind
 	// a put batch on `st` nor take `mu`
-	cudaStream_t gst = nullptr;
-	std::mutex get_mu;
-	unsigned long long *d_gaddr = nullptr;
-	int32_t *h_gstatus = nullptr;                // page-locked, the kernel writes it directly
-	cmb200_addr *h_gaddr = nullptr;
+	// Several small gets may be in flight at once (two leader threads of the combining queue, or any
+	// callers of cmb200_get_small): each takes one LANE — a stream plus page-locked request / status
+	// words — and the shared side of get_rw; what moves records or peer mappings (compaction, peers,
+	// destroy) takes get_rw exclusively.
+	static constexpr int GET_LANES = 4;
+	struct GetLane { std::mutex mu; cudaStream_t st = nullptr; int32_t *h_status = nullptr; cmb200_addr *h_addr = nullptr; };
+	GetLane lane[GET_LANES];
+	std::shared_mutex get_rw;
+	std::atomic<uint32_t> lane_turn{0};
 	static constexpr size_t GET_SMALL_MAX = 1024;
 	const uint8_t *peer_base[GET_MAX_PEERS] = {};
 	uint64_t peer_size[GET_MAX_PEERS] = {};
-	uint64_t small_get_requests = 0, small_get_hits = 0, small_get_launches = 0;
+	std::atomic<uint64_t> small_get_requests{0}, small_get_hits{0}, small_get_launches{0};
 	unsigned long long *d_recoff_out = nullptr;  // arena offset per chunk of the current put slice (exchange records)
 	cudaEvent_t landed[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr};
 	TableView table{};
@@ -132,11 +138,13 @@ extern "C" void cmb200_engine_destroy(cmb200_engine *e) {
 	cudaFree(e->d_pages[0]); cudaFree(e->d_pages[1]); cudaFree(e->d_stage);
 	cudaFree(e->d_addr); cudaFree(e->d_ts); cudaFree(e->d_valid); cudaFree(e->d_slot); cudaFree(e->d_vlen);
 	if (e->h_meta) cudaFreeHost(e->h_meta);
-	if (e->h_gstatus) cudaFreeHost(e->h_gstatus);
-	if (e->h_gaddr) cudaFreeHost(e->h_gaddr);
-	cudaFree(e->d_gaddr); cudaFree(e->d_recoff_out);
+	for (auto &ln : e->lane) {
+		if (ln.st) { cudaStreamSynchronize(ln.st); cudaStreamDestroy(ln.st); }
+		if (ln.h_status) cudaFreeHost(ln.h_status);
+		if (ln.h_addr) cudaFreeHost(ln.h_addr);
+	}
+	cudaFree(e->d_recoff_out);
 	for (int r = 0; r < GET_MAX_PEERS; r++) if (e->peer_base[r]) cudaIpcCloseMemHandle((void *)e->peer_base[r]);
-	if (e->gst) { cudaStreamSynchronize(e->gst); cudaStreamDestroy(e->gst); }
 	cudaFree(e->d_lens); cudaFree(e->d_status); cudaFree(e->d_fps); cudaFree(e->d_recoff); cudaFree(e->d_work); cudaFree(e->d_import_slot);
 	for (int i = 0; i < 2; i++) {
 		if (e->landed[i]) cudaEventDestroy(e->landed[i]);
@@ -185,7 +193,7 @@ extern "C" cmb200_engine *cmb200_engine_create(const cmb200_config *cfg) {
 		e->table.cap = slots;
 		ENG_CHECK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
 		ENG_CHECK(cudaStreamCreateWithFlags(&e->copy, cudaStreamNonBlocking));
-		ENG_CHECK(cudaStreamCreateWithFlags(&e->gst, cudaStreamNonBlocking));
+		for (auto &ln : e->lane) ENG_CHECK(cudaStreamCreateWithFlags(&ln.st, cudaStreamNonBlocking));
 		for (int i = 0; i < 2; i++) {
 			ENG_CHECK(cudaEventCreateWithFlags(&e->landed[i], cudaEventDisableTiming));
 			ENG_CHECK(cudaEventCreateWithFlags(&e->consumed[i], cudaEventDisableTiming));
@@ -238,9 +246,10 @@ extern "C" cmb200_engine *cmb200_engine_create(const cmb200_config *cfg) {
 		ENG_CHECK(cudaMalloc(&e->d_recoff, B * 8));
 		ENG_CHECK(cudaMalloc(&e->d_work, 64));
 		ENG_CHECK(cudaMallocHost(&e->h_meta, cmb200_engine::META_CAP * 33));
-		ENG_CHECK(cudaMalloc(&e->d_gaddr, cmb200_engine::GET_SMALL_MAX * 16));
-		ENG_CHECK(cudaMallocHost(&e->h_gstatus, cmb200_engine::GET_SMALL_MAX * 4));
-		ENG_CHECK(cudaMallocHost(&e->h_gaddr, cmb200_engine::GET_SMALL_MAX * 16));
+		for (auto &ln : e->lane) {
+			ENG_CHECK(cudaMallocHost(&ln.h_status, cmb200_engine::GET_SMALL_MAX * 4));
+			ENG_CHECK(cudaMallocHost(&ln.h_addr, cmb200_engine::GET_SMALL_MAX * 16));
+		}
 		ENG_CHECK(cudaMalloc(&e->d_recoff_out, M * 8));
 
 		uint64_t arena = cfg->arena_bytes;
@@ -671,53 +680,65 @@ extern "C" int cmb200_import_remote(cmb200_engine *e, size_t n, const cmb200_add
 extern "C" int cmb200_get_small(cmb200_engine *e, size_t n, const cmb200_addr *addr, void *pages_out, int32_t *status_out) {
 	if (n == 0) return 0;
 	if (!get_small_supports(e->bsize)) { set_error_msg("cmb200_get_small: page size not supported by the fused kernel"); return -2; }
-	std::lock_guard<std::mutex> g(e->get_mu);
+	std::shared_lock<std::shared_mutex> shared(e->get_rw);
+	// a free lane if there is one, else wait for the next in turn
+	cmb200_engine::GetLane *ln = nullptr;
+	std::unique_lock<std::mutex> lk;
+	const uint32_t first = e->lane_turn.fetch_add(1, std::memory_order_relaxed);
+	for (int k = 0; k < cmb200_engine::GET_LANES && !ln; k++) {
+		cmb200_engine::GetLane &c = e->lane[(first + k) % cmb200_engine::GET_LANES];
+		std::unique_lock<std::mutex> t(c.mu, std::try_to_lock);
+		if (t.owns_lock()) { ln = &c; lk = std::move(t); }
+	}
+	if (!ln) { ln = &e->lane[first % cmb200_engine::GET_LANES]; lk = std::unique_lock<std::mutex>(ln->mu); }
 	CMB_CHECK(cudaSetDevice(e->device));
 	static const int32_t PENDING = -1;
+	uint64_t rq = 0, ht = 0;
 	for (size_t at = 0; at < n; at += cmb200_engine::GET_SMALL_MAX) {
 		const uint32_t m = (uint32_t)((n - at < cmb200_engine::GET_SMALL_MAX) ? n - at : cmb200_engine::GET_SMALL_MAX);
 		// Requests and answers travel through page-locked host memory that the kernel reads and writes
 		// directly: no copy is queued before or after the launch, and the caller learns of the end by
 		// watching the status words flip (the kernel writes a page, fences, then its status), which costs
 		// a few microseconds where a stream synchronisation costs tens.
-		memcpy(e->h_gaddr, addr + at, (size_t)m * 16);
-		for (uint32_t i = 0; i < m; i++) ((volatile int32_t *)e->h_gstatus)[i] = PENDING;
+		memcpy(ln->h_addr, addr + at, (size_t)m * 16);
+		volatile int32_t *hs = ln->h_status;
+		for (uint32_t i = 0; i < m; i++) hs[i] = PENDING;
 		GetJob job{};
 		job.table = e->table; job.arena = e->arena.base; job.arena_size = e->arena.size;
-		job.addr = (const unsigned long long *)e->h_gaddr; job.valid = nullptr; job.n = m; job.nbytes = e->bsize;
+		job.addr = (const unsigned long long *)ln->h_addr; job.valid = nullptr; job.n = m; job.nbytes = e->bsize;
 		job.out = (uint8_t *)pages_out + at * e->bsize;          // device memory or page-locked host memory (UVA)
-		job.status = e->h_gstatus;
+		job.status = ln->h_status;
 		for (int r = 0; r < GET_MAX_PEERS; r++) { job.peer[r] = e->peer_base[r]; job.peer_size[r] = e->peer_size[r]; }
-		if (launch_get_small(job, e->gst)) return -1;
+		if (launch_get_small(job, ln->st)) return -1;
 		uint32_t done = 0;
 		for (uint64_t spins = 0; done < m;) {
-			if (((volatile int32_t *)e->h_gstatus)[done] != PENDING) { done++; continue; }
+			if (hs[done] != PENDING) { done++; continue; }
 #if defined(__x86_64__)
 			__builtin_ia32_pause();
 #endif
 			if (++spins > 20000) {                                // ~1 ms of polling: a large batch, let the driver wait
-				CMB_CHECK(cudaStreamSynchronize(e->gst));
+				CMB_CHECK(cudaStreamSynchronize(ln->st));
 				spins = 0;
-				if (((volatile int32_t *)e->h_gstatus)[done] == PENDING) { set_error_msg("cmb200_get_small: kernel finished without an answer"); return -1; }
+				if (hs[done] == PENDING) { set_error_msg("cmb200_get_small: kernel finished without an answer"); return -1; }
 			}
 		}
 		__atomic_thread_fence(__ATOMIC_ACQUIRE);
-		memcpy(status_out + at, e->h_gstatus, (size_t)m * 4);
-		e->small_get_launches++;
+		memcpy(status_out + at, ln->h_status, (size_t)m * 4);
 		for (uint32_t i = 0; i < m; i++) {
-			if (status_out[at + i] != CMB200_INVALID) e->small_get_requests++;
-			if (status_out[at + i] == CMB200_HIT) e->small_get_hits++;
+			if (status_out[at + i] != CMB200_INVALID) rq++;
+			if (status_out[at + i] == CMB200_HIT) ht++;
 		}
+		e->small_get_launches++;
 	}
+	e->small_get_requests += rq; e->small_get_hits += ht;
 	return 0;
 }
 
 // ---- peers: the other ranks' arenas, mapped for NVLink reads -------------------------------------
 
 extern "C" int cmb200_close_peers(cmb200_engine *e) {
-	std::lock_guard<std::mutex> g(e->get_mu);
+	std::unique_lock<std::shared_mutex> g(e->get_rw);      // no small get in flight
 	CMB_CHECK(cudaSetDevice(e->device));
-	CMB_CHECK(cudaStreamSynchronize(e->gst));
 	for (int r = 0; r < GET_MAX_PEERS; r++) {
 		if (e->peer_base[r]) cudaIpcCloseMemHandle((void *)e->peer_base[r]);
 		e->peer_base[r] = nullptr; e->peer_size[r] = 0;
@@ -737,7 +758,7 @@ extern "C" int cmb200_arena_ipc_handle(cmb200_engine *e, void *handle64, uint64_
 
 extern "C" int cmb200_open_peer(cmb200_engine *e, uint32_t rank, const void *handle64, uint64_t arena_bytes) {
 	if (rank >= GET_MAX_PEERS) { set_error_msg("cmb200_open_peer: rank out of range"); return -1; }
-	std::lock_guard<std::mutex> g(e->get_mu);
+	std::unique_lock<std::shared_mutex> g(e->get_rw);
 	CMB_CHECK(cudaSetDevice(e->device));
 	cudaIpcMemHandle_t h;
 	memcpy(&h, handle64, 64);
@@ -784,11 +805,8 @@ extern "C" int cmb200_get_stats(cmb200_engine *e, cmb200_stats *out) {
 	if (read_counters(e, c)) return -1;
 	harvest_pending(e, true);
 	*out = e->stats;
-	{
-		std::lock_guard<std::mutex> gg(e->get_mu);
-		out->get_requests += e->small_get_requests; out->get_hits += e->small_get_hits;
-		out->kernel_launches += e->small_get_launches;
-	}
+	out->get_requests += e->small_get_requests.load(); out->get_hits += e->small_get_hits.load();
+	out->kernel_launches += e->small_get_launches.load();
 	out->entries = c[0]; out->tombstones = c[1];
 	out->arena_used = c[2] < e->arena.size ? c[2] : e->arena.size;   // the bump pointer saturates past the end (no rollback)
 	out->arena_garbage = c[3];
@@ -1021,7 +1039,7 @@ extern "C" int cmb200_load(cmb200_engine *e, const char *path, uint64_t *records
 // to overflow although a good part of it is garbage (filemap_make_room, cmb200_compact).
 extern "C" int cmb200_compact(cmb200_engine *e, uint64_t *reclaimed_out) {
 	std::lock_guard<std::mutex> g(e->mu);
-	std::lock_guard<std::mutex> gg(e->get_mu);       // records move: no small get may be reading the arena
+	std::unique_lock<std::shared_mutex> gg(e->get_rw);  // records move: no small get may be reading the arena
 	unsigned long long c[8];
 	if (read_counters(e, c)) return -1;
 	harvest_pending(e, true);
@@ -1063,6 +1081,27 @@ extern "C" int cmb200_compact(cmb200_engine *e, uint64_t *reclaimed_out) {
 	CMB_CHECK(cudaMemsetAsync(e->arena.seg, 0, ARENA_SEG_SLOTS * 2 * sizeof(unsigned long long), e->st));
 	CMB_CHECK(cudaStreamSynchronize(e->st));
 	if (reclaimed_out) *reclaimed_out = head_before > at ? head_before - at : 0;
+	// The table is rebuilt on the same occasion when deleted keys have eaten a good part of its empty
+	// slots (tombstones; slots of dropped puts go with them): miss probes end at an EMPTY slot, and
+	// linear probing never frees one by itself.
+	if (c[1] > e->table.cap / 8) {
+		TableView fresh = e->table;
+		fresh.slots = nullptr; fresh.fp = nullptr;
+		if (cudaMalloc(&fresh.slots, (e->table.cap + 2) * sizeof(Slot)) == cudaSuccess &&
+		    (!e->table.fp || cudaMalloc(&fresh.fp, (e->table.cap + 2) * 16) == cudaSuccess)) {
+			CMB_CHECK(cudaMemsetAsync(fresh.slots, 0, (e->table.cap + 2) * sizeof(Slot), e->st));
+			if (fresh.fp) CMB_CHECK(cudaMemsetAsync(fresh.fp, 0, (e->table.cap + 2) * 16, e->st));
+			if (launch_rehash(e->table, fresh, e->st)) return -1;
+			CMB_CHECK(cudaMemsetAsync(e->d_counters + 1, 0, sizeof(unsigned long long), e->st));   // tombstones
+			CMB_CHECK(cudaStreamSynchronize(e->st));
+			cudaFree(e->table.slots); cudaFree(e->table.fp);
+			e->table.slots = fresh.slots; e->table.fp = fresh.fp;
+			e->stats.kernel_launches++;
+		} else {
+			(void)cudaGetLastError();                    // no room for a second table: keep the old one
+			cudaFree(fresh.slots);
+		}
+	}
 	return 0;
 }
 

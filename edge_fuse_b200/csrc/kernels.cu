@@ -714,7 +714,7 @@ int launch_encode(const EncodeJob &job_in, cudaStream_t st) {
 // decode
 // ------------------------------------------------------------------------------------------
 
-__global__ void __launch_bounds__(256) k_decode(DecodeJob job) {
+__global__ void __launch_bounds__(256, 8) k_decode(DecodeJob job) {
 	const int lane = threadIdx.x & 31;
 	const uint32_t i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
 	if (i >= job.n) return;
@@ -1166,6 +1166,35 @@ int launch_compact_window(TableView t, ArenaView a, const MoveEntry *moves, uint
 	k_compact_gather<<<(n * 32 + 255) / 256, 256, 0, st>>>(a, moves, n, bounce);
 	CMB_CHECK(cudaGetLastError());
 	k_compact_scatter<<<(n * 32 + 255) / 256, 256, 0, st>>>(t, a, moves, n, bounce);
+	CMB_CHECK(cudaGetLastError());
+	return 0;
+}
+
+// ---- table rebuild ---------------------------------------------------------------------------
+// Linear probing never gives a slot back: a deleted key leaves a tombstone and a key whose put was
+// dropped leaves a claimed slot without a record, so over a long run the EMPTY slots only shrink and
+// miss probes walk ever longer chains.  The rebuild re-inserts what is alive (a local record or a
+// remote owner) into a fresh table of the same size; everything else disappears.
+__global__ void k_rehash(TableView from, TableView to) {
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= from.cap + 2) return;
+	const Slot s = from.slots[i];
+	if (s.vlen == 0 && s.owner == 0) return;
+	if (i < from.cap && (s.key == KEY_EMPTY || s.key == KEY_TOMB)) return;
+	const unsigned long long key = i < from.cap ? s.key : (i == from.cap ? KEY_EMPTY : KEY_TOMB);
+	const uint32_t idx = table_find_or_claim(to, key);
+	if (idx == 0xffffffffu) return;                     // cannot happen: same size, fewer keys
+	Slot d = s;
+	d.key = idx < to.cap ? key : 0ull;
+	// the key word was written by the claim; copy the rest field by field so that it is not torn
+	Slot &t = to.slots[idx];
+	t.addr_u = d.addr_u; t.addr_l = d.addr_l; t.rec_off = d.rec_off; t.vlen = d.vlen; t.alloc = d.alloc;
+	t.ts = d.ts; t.seq = d.seq; t.owner = d.owner;
+	if (from.fp && to.fp) { to.fp[2 * (size_t)idx] = from.fp[2 * i]; to.fp[2 * (size_t)idx + 1] = from.fp[2 * i + 1]; }
+}
+int launch_rehash(TableView from, TableView to, cudaStream_t st) {
+	const uint64_t n = from.cap + 2;
+	k_rehash<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(from, to);
 	CMB_CHECK(cudaGetLastError());
 	return 0;
 }

@@ -197,6 +197,9 @@ static_assert(sizeof(MoveEntry) == 24, "move entry layout");
 int launch_compact_window(TableView t, ArenaView a, const MoveEntry *moves, uint32_t n, uint8_t *bounce,
     cudaStream_t st);
 
+// Re-inserts every live slot of `from` into the (zeroed) table `to` of the same geometry.
+int launch_rehash(TableView from, TableView to, cudaStream_t st);
+
 int sm_count();
 
 }  // namespace cmb

@@ -229,7 +229,7 @@ __device__ __noinline__ uint32_t lz4_emit_general(uint8_t *dst, uint32_t op, con
 	op++;
 	if (lit >= 15u) op = lz4_emit_len(dst, op, lit - 15u, lane);
 	if (lit <= 256u) {           // the usual case here is a run of 65..200 bytes: bytes, no alignment work
-		for (uint32_t i = lane; i < lit; i += 32) dst[op + i] = (uint8_t)ldg8(src + anchor + i);
+		for (uint32_t i = lane; i < lit; i += 32) st_out8(dst + op + i, ldg8(src + anchor + i));
 	} else {
 		warp_copy_ro(dst + op, src + anchor, lit, lane);
 	}

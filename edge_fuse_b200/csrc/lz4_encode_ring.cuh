@@ -323,14 +323,14 @@ __device__ uint32_t lz4_encode_lean(const uint8_t *__restrict__ src, uint32_t n,
 				uint8_t *o = dst + op;
 				const uint32_t lext = lit >= 15u, mext = mc >= 15u;
 				const uint32_t hl = 1u + lext;
-				if ((uint32_t)lane < lit) o[hl + lane] = (uint8_t)litbyte;
-				if ((uint32_t)lane + 32u < lit) o[hl + 32u + lane] = (uint8_t)litbyte2;
+				if ((uint32_t)lane < lit) st_out8(o + hl + lane, litbyte);
+				if ((uint32_t)lane + 32u < lit) st_out8(o + hl + 32u + lane, litbyte2);
 				const uint32_t tail = hl + lit;
 				const uint32_t head4 = (min(lit, 15u) << 4) | min(mc, 15u) | (((lit - 15u) & 0xffu) << 8) | (off << 16);
 				const uint32_t val = lane < 4 ? head4 >> (8u * (uint32_t)lane) : mc - 15u;
 				const uint32_t at = lane < 2 ? (uint32_t)lane : tail + (uint32_t)lane - 2u;
 				const uint32_t owners = 0x0du | (lext << 1) | (mext << 4);
-				if ((owners >> lane) & 1u) o[at] = (uint8_t)val;
+				if ((owners >> lane) & 1u) st_out8(o + at, val);
 				op += tail + 2u + mext;
 			} else {
 				op = lz4_emit_general(dst, op, src, anchor, lit, off, mc, lane);

@@ -976,3 +976,37 @@ def test_cache_directory_interchange_with_the_reference(E, gpu, oracle, tmp_path
     got, hit = cm2.get_batch(off, np.full(n, 99, dtype=np.uint64), np.full(n, 7, dtype=np.uint32))
     assert hit.all() and (got == pages[::-1]).all()
     cm2.free()
+
+
+@pytest.mark.gpu
+def test_compaction_rebuilds_a_table_full_of_tombstones(E, gpu):
+    """Linear probing never returns a slot: after many deletes the table is mostly tombstones.
+    cmb200_compact then rebuilds it; every live key, its record, timestamp order and the counters
+    survive, deleted keys stay deleted, and new keys can be put afterwards."""
+    eng = E.Engine(pshift=12, accel=12, capacity=1024, table_slots=4096, arena_bytes=64 << 20, max_batch=512, flags=E.FINGERPRINT)
+    assert eng.stats()["table_slots"] == 4096
+    pages = np.stack([datagen.make_page("T", 4096, i) for i in range(512)])
+    keep_u = np.full(300, 3, dtype=np.uint64); keep_l = np.arange(300, dtype=np.uint64)
+    eng.put(keep_u, keep_l, pages[:300], ts=np.arange(300, dtype=np.uint64) + 1)
+    for rnd in range(8):                                   # 8 x 400 keys put and deleted again
+        u = np.full(400, 100 + rnd, dtype=np.uint64); l = np.arange(400, dtype=np.uint64)
+        eng.put(u, l, pages[:400]); eng.unset(u, l)
+    before = eng.stats()
+    assert before["tombstones"] > 4096 // 8 and before["entries"] == 300
+    fps0, ok0 = eng.read_fingerprints(keep_u, keep_l)
+    eng.compact()
+    after = eng.stats()
+    assert after["tombstones"] == 0 and after["entries"] == 300 and after["arena_garbage"] == 0
+    out, st = eng.get(keep_u, keep_l)
+    assert (st == E.HIT).all() and (out == pages[:300]).all()
+    out, st = eng.get_small(keep_u, keep_l)
+    assert (st == E.HIT).all() and (out == pages[:300]).all()
+    fps1, ok1 = eng.read_fingerprints(keep_u, keep_l)
+    assert (ok0 == ok1).all() and (fps0 == fps1).all()
+    _, st = eng.get(np.full(400, 103, dtype=np.uint64), np.arange(400, dtype=np.uint64))
+    assert (st == E.MISS).all()
+    u = np.full(200, 500, dtype=np.uint64); l = np.arange(200, dtype=np.uint64)
+    eng.put(u, l, pages[200:400])
+    out, st = eng.get(u, l)
+    assert (st == E.HIT).all() and (out == pages[200:400]).all() and eng.stats()["entries"] == 500
+    eng.close()
