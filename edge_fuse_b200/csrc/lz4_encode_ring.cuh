@@ -206,6 +206,22 @@ __device__ uint32_t lz4_encode_lean(const uint8_t *__restrict__ src, uint32_t n,
 		// them from the lane number on the critical path of every iteration)
 		asm volatile("" : "+r"(delta2), "+r"(en_below));
 		bool started = false;                                              // a match has ended (uniform)
+		// Batch width.  Only the lanes up to the first hit matter; the rest of the 30 speculative probes
+		// are table traffic and — worse — scattered candidate reads, most of which miss the L1 and
+		// occupy the SM's outstanding-request slots (text-like pages find their match within the first
+		// few probes).  So a chunk whose recent batches all hit early runs 16-lane batches (refill,
+		// re-test, 14 probes); a 16-lane batch that finds nothing continues in lz4_search_slow from slot
+		// 16 and the chunk goes back to 32 lanes for a while.  Same probes in the same order either way.
+#ifndef CMB_LZ4_NARROW
+#define CMB_LZ4_NARROW 1
+#endif
+#ifndef CMB_LZ4_NARROW_W
+#define CMB_LZ4_NARROW_W 16u
+#endif
+#ifndef CMB_LZ4_NARROW_HIT
+#define CMB_LZ4_NARROW_HIT 12
+#endif
+		uint32_t width = 32u, calm = 0u;                                    // lanes per batch; batches in a row that hit below lane 12
 		uint32_t next_event = 0;                                           // anchor at which the frontiers move next
 		for (;;) {
 			if (anchor >= next_event) {
@@ -237,7 +253,7 @@ __device__ uint32_t lz4_encode_lean(const uint8_t *__restrict__ src, uint32_t n,
 				}
 				if (FP) fp.upto(src, anchor + 512u, lane);
 			}
-			const bool en = anchor < en_below;
+			const bool en = anchor < en_below && (uint32_t)lane < width;
 			const uint32_t pos = en ? anchor + delta2 : 0u;        // disabled lanes read (and ignore) position 0 / ring offset 0
 			// speculative literal bytes: src[anchor + lane], src[anchor + 32 + lane] (used when the run is <= 64 bytes;
 			// never stored beyond the literal run, so reading past the page end is harmless in the ring)
@@ -291,6 +307,10 @@ __device__ uint32_t lz4_encode_lean(const uint8_t *__restrict__ src, uint32_t n,
 				fwd = __shfl_sync(CMB_FULL, nf, w);
 				back = __shfl_sync(CMB_FULL, nb, w);
 				retest_hit = w == 1;
+				if (CMB_LZ4_NARROW) {
+					calm = w < CMB_LZ4_NARROW_HIT ? calm + 1u : 0u;
+					if (w >= CMB_LZ4_NARROW_HIT) width = 32u; else if (calm >= 8u) width = CMB_LZ4_NARROW_W;
+				}
 				if (fwd == 4u || back == 4u) {                      // longer than the neighbourhoods show: rare
 					if (fwd == 4u) fwd = 4u + lz4_count_long(src, ip + 8u, match + 8u, mlimit, lim4, lane);
 					if (back == 4u && ip >= anchor + 5u && match >= 5u)
@@ -298,13 +318,16 @@ __device__ uint32_t lz4_encode_lean(const uint8_t *__restrict__ src, uint32_t n,
 				}
 			} else {
 				uint64_t res = 0;
-				const uint32_t enmask = __ballot_sync(CMB_FULL, en || special);
+				// lanes of this batch that were held back only by the end margin (not by the batch width)
+				const uint32_t enmask = __ballot_sync(CMB_FULL, en || special || (uint32_t)lane >= width);
+				const uint32_t w0 = width;
+				if (CMB_LZ4_NARROW) { width = 32u; calm = 0u; }
 				if (foreigns) {
 					if (en) tab.put(h, cand);
 					__syncwarp();
 					res = lz4_search_slow<WIDE>(src, lim4, tab, anchor, 2u, accel, mflimit, 0, lane, started);
-				} else if (enmask == CMB_FULL) {                     // 30 probes were not enough
-					res = lz4_search_slow<WIDE>(src, lim4, tab, anchor, 2u, accel, mflimit, 32, lane, started);
+				} else if (enmask == CMB_FULL) {                     // the probes of this batch were not enough
+					res = lz4_search_slow<WIDE>(src, lim4, tab, anchor, 2u, accel, mflimit, w0, lane, started);
 				}
 				if (!(res >> 63)) break;                             // -> last literals
 				retest_hit = (res >> 62) & 1u;
