@@ -32,8 +32,10 @@
 #include "../../include/cachemap.h"
 #include "../../include/cachemap_b200.h"
 
-#define COMBINE_MAX 256         /* get/unset requests one leader takes per GPU batch */
-#define LEADERS 2               /* batches of gets that may be in flight at once (each on its own engine lane) */
+#define COMBINE_MAX 32          /* get/unset requests one leader takes per GPU batch */
+#define LEADERS 16              /* batches of gets that may be in flight at once (each on its own engine lane):
+                                 * a get's latency is one chunk's decode, so requests are combined only when more
+                                 * than LEADERS callers are waiting; a B200 decodes 148 pages at a time */
 #define FLUSH_MAX 1024          /* pages the flusher hands over per GPU batch */
 #define PNUM_SHIFT 44           /* cachemap.c:155 */
 

@@ -48,7 +48,7 @@ struct cmb200_engine {
 	// callers of cmb200_get_small): each takes one LANE — a stream plus page-locked request / status
 	// words — and the shared side of get_rw; what moves records or peer mappings (compaction, peers,
 	// destroy) takes get_rw exclusively.
-	static constexpr int GET_LANES = 4;
+	static constexpr int GET_LANES = 16;
 	struct GetLane { std::mutex mu; cudaStream_t st = nullptr; int32_t *h_status = nullptr; cmb200_addr *h_addr = nullptr; };
 	GetLane lane[GET_LANES];
 	std::shared_mutex get_rw;

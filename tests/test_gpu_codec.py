@@ -233,3 +233,20 @@ print("group-mode parity ok")
     out = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, CMB200_ENC_MODE="1"),
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "group-mode parity ok" in out.stdout, out.stdout + out.stderr
+
+
+@pytest.mark.gpu
+def test_cuda_blocks_equal_the_compiled_reference_directly(E, gpu, oracle):
+    """CUDA == reference without the port in between: blocks and lengths of the GPU encoder against
+    LZ4_compress_fast of oracle/_ref (the reference's own lz4.c compiled by oracle/Makefile), every
+    content class, 64 KiB and 4 KiB pages, and the reference's LZ4_decompress_fast decodes them back."""
+    if oracle.ref() is None:
+        pytest.skip("oracle/_ref was not built (needs /root/reference in the authoring container)")
+    for bs, n in ((65536, 84), (4096, 140)):
+        pages = np.stack([datagen.make_page("RTZMPAX"[i % 7], bs, 9000 + i) for i in range(n)])
+        blocks, _ = E.lz4_encode_batch(pages, accel=12)
+        for i in range(n):
+            want = oracle.ref_lz4_encode(pages[i], 12)
+            assert blocks[i] == want, (bs, i)
+            back, used = oracle.ref_lz4_decode(want, bs)
+            assert used == len(want) and back == pages[i].tobytes()
