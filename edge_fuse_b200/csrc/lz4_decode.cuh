@@ -135,7 +135,13 @@ __device__ __forceinline__ bool lz4_read_ext_smem(const uint8_t *blk, uint32_t c
 // Same result as LZ4_decompress_fast (lz4.c:1169-1344,1360-1363): exactly n bytes decoded, return
 // value = bytes of the block consumed (lz4.c:1339), or negative for a malformed block.
 constexpr uint32_t DQ = 64;                       // descriptor ring entries
-constexpr uint32_t DQ_PUBLISH = 4;                // counters move every DQ_PUBLISH sequences
+#ifndef CMB_DQ_PUBLISH
+#define CMB_DQ_PUBLISH 4
+#endif
+#ifndef CMB_DP_SLEEP
+#define CMB_DP_SLEEP 0
+#endif
+constexpr uint32_t DQ_PUBLISH = CMB_DQ_PUBLISH;   // counters move every DQ_PUBLISH sequences
 struct DecodePipe {
 	uint4 q[DQ];                              // {lit_src, out_pos, lit_len, off | (match_len - 4) << 16}; off 0 = last sequence
 	uint32_t parsed;                          // sequences published
@@ -161,7 +167,14 @@ __device__ __forceinline__ void sst128(uint32_t a, uint4 v) {
 // get reports a decode error instead of hanging the CTA (cannot happen with a consistent ring; it
 // bounds the damage of a bug or of corrupted shared state).
 constexpr uint32_t DP_SPIN_LIMIT = 1u << 26;
-__device__ __forceinline__ uint32_t sld_flag(uint32_t a) { uint32_t v; asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ uint32_t sld_flag(uint32_t a) {
+	uint32_t v;
+	asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+#if CMB_DP_SLEEP
+	__nanosleep(CMB_DP_SLEEP);              // a waiting stage backs off: its polls compete with the working stages for the shared-memory pipe
+#endif
+	return v;
+}
 __device__ __forceinline__ void sst_flag(uint32_t a, uint32_t v) { asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
 // length extension at shared address blk + ip (LZ4 255-run rule); cap = block length
@@ -195,6 +208,34 @@ __device__ void lz4_pipe_parse(uint32_t dp, uint32_t blk, uint32_t cap, uint32_t
 	// the block buffer is padded, so reading a few bytes past `cap` is safe; every use is bounds-checked
 	uint32_t tok = res ? 0u : sld8(blk), b0 = res ? 0u : sld8(blk + 1u);
 	while (res == 0) {
+		// ---- the common sequence, straight line: literal and match lengths with at most one extension
+		// byte each, everything inside the block and the page, a free ring slot.  Anything else — longer
+		// extensions, the last sequence, a malformed block, a full ring — is ONE rarely taken branch to
+		// the general code below, which re-derives the sequence from (tok, b0, ip, op).
+		{
+			const uint32_t l4 = tok >> 4, m4 = tok & 15u;
+			const uint32_t lx = l4 == 15u ? 1u : 0u, mx = m4 == 15u ? 1u : 0u;
+			const uint32_t flen = l4 + (lx ? b0 : 0u);
+			const uint32_t fsrc = ip + 1u + lx;
+			const uint32_t ip2 = fsrc + flen, op2 = op + flen;           // offset bytes; output after the literals
+			const uint32_t a = blk + min(ip2, cap);                       // (clamped: the rare path rejects what lies outside)
+			const uint32_t o0 = sld8(a), o1 = sld8(a + 1u), m0 = sld8(a + 2u);
+			const uint32_t nip = ip2 + 2u + mx;
+			const uint32_t an = blk + min(nip, cap);
+			const uint32_t t1 = sld8(an), t2 = sld8(an + 1u);
+			const uint32_t off = o0 | (o1 << 8);
+			const uint32_t fm = m4 + (mx ? m0 : 0u);
+			const uint32_t op3 = op2 + fm + 4u;
+			const bool rare = ip + 2u >= cap || (lx && b0 == 255u) || (mx && m0 == 255u) || nip > cap || op2 + 8u > n ||
+			    off == 0u || off > op2 || op3 + 5u > n || s >= freed + DQ;
+			if (!rare) {
+				if (lane == 0) sst128(dp + (s % DQ) * 16u, make_uint4(fsrc, op, flen, off | (fm << 16)));
+				s++;
+				if (lane == 0 && (s % DQ_PUBLISH) == 0u) sst_flag(a_parsed, s);   // same lane wrote the entries: ordered
+				ip = nip; op = op3; tok = t1; b0 = t2;
+				continue;
+			}
+		}
 		if (ip >= cap) { res = -1; break; }
 		uint32_t len = tok >> 4, mlen = tok & 15u;
 		uint32_t lit_src = ip + 1u;
@@ -267,6 +308,7 @@ __device__ void lz4_pipe_literals(uint32_t dp, uint32_t blk, uint32_t out, const
 		}
 		if (ended) return;
 		const uint4 d = sld128(dp + (s % DQ) * 16u);
+#ifndef CMB_DP_SKIP_LIT      /* diagnostic builds only: the stage consumes its descriptors without copying */
 		if (d.z <= 32u) {
 			if ((uint32_t)lane < d.z) sst8(out + d.y + (uint32_t)lane, sld8(blk + d.x + (uint32_t)lane));
 		} else if (d.z < 256u) {
@@ -274,6 +316,7 @@ __device__ void lz4_pipe_literals(uint32_t dp, uint32_t blk, uint32_t out, const
 		} else {
 			warp_copy_rw(out_g + d.y, blk_g + d.x, d.z, lane);   // long runs: 16 bytes per lane per step
 		}
+#endif
 		const bool last = (d.w & 0xffffu) == 0u;
 		__syncwarp();
 		if (lane == 0) { sst_flag(a_lit, mine + 1u); if (last) sst_flag(a_parsed + 28u, 1u); }
@@ -300,6 +343,7 @@ __device__ void lz4_pipe_matches(uint32_t dp, uint32_t out, int lane) {
 		}
 		if (off == 0u) { if (lane == 0) sst_flag(a_mat, s + 1u); return; }
 		const uint32_t to = out + d.y + d.z, from = to - off;
+#ifndef CMB_DP_SKIP_MATCH    /* diagnostic builds only */
 		if (off >= len) {
 			if (len <= 32u) { if ((uint32_t)lane < len) sst8(to + (uint32_t)lane, sld8(from + (uint32_t)lane)); }
 			else for (uint32_t k = lane; k < len; k += 32u) sst8(to + k, sld8(from + k));
@@ -314,6 +358,7 @@ __device__ void lz4_pipe_matches(uint32_t dp, uint32_t out, int lane) {
 				if (r >= off) r -= off;
 			}
 		}
+#endif
 		__syncwarp();                                        // the next match may read what this one wrote
 		if (((s + 1u) % DQ_PUBLISH) == 0u && lane == 0) sst_flag(a_mat, s + 1u);
 	}
