@@ -38,7 +38,7 @@ def _newer(src_paths, target) -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """CMB200_NVCC_EXTRA (e.g. "-DCMB_OUT_HINT=1") adds compile flags and CMB200_BUILD_OUT names the
+    """CMB200_NVCC_EXTRA (e.g. "-DCMB_OUT_HINT=1") adds nvcc flags (CMB200_CC_EXTRA: flags for the C layer) and CMB200_BUILD_OUT names the
     output file: a differently tuned build of the same library next to the default one, loaded by
     setting CMB200_LIB (tuning experiments; the default build takes neither)."""
     global LIB, OBJ
@@ -64,7 +64,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         objs.append(obj)
     for src in C_SOURCES:
         obj = os.path.join(OBJ, src.replace(".c", ".o"))
-        subprocess.run(["gcc", "-std=gnu11", "-O2", "-fPIC", "-Wall", "-Wextra", "-pthread", "-c",
+        subprocess.run(["gcc", "-std=gnu11", "-O2", "-fPIC", "-Wall", "-Wextra", "-pthread",
+                        *os.environ.get("CMB200_CC_EXTRA", "").split(), "-c",
                         os.path.join(CSRC, src), "-o", obj], check=True)
         objs.append(obj)
     subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs,

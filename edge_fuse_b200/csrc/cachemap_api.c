@@ -33,7 +33,9 @@
 #include "../../include/cachemap_b200.h"
 
 #define COMBINE_MAX 32          /* get/unset requests one leader takes per GPU batch */
-#define LEADERS 16              /* batches of gets that may be in flight at once (each on its own engine lane):
+#ifndef LEADERS
+#define LEADERS 16
+#endif                          /* batches of gets that may be in flight at once (each on its own engine lane):
                                  * a get's latency is one chunk's decode, so requests are combined only when more
                                  * than LEADERS callers are waiting; a B200 decodes 148 pages at a time */
 #define FLUSH_MAX 1024          /* pages the flusher hands over per GPU batch */

@@ -48,7 +48,10 @@ struct cmb200_engine {
 	// callers of cmb200_get_small): each takes one LANE — a stream plus page-locked request / status
 	// words — and the shared side of get_rw; what moves records or peer mappings (compaction, peers,
 	// destroy) takes get_rw exclusively.
-	static constexpr int GET_LANES = 16;
+#ifndef CMB_GET_LANES
+#define CMB_GET_LANES 16
+#endif
+	static constexpr int GET_LANES = CMB_GET_LANES;
 	struct GetLane { std::mutex mu; cudaStream_t st = nullptr; int32_t *h_status = nullptr; cmb200_addr *h_addr = nullptr; };
 	GetLane lane[GET_LANES];
 	std::shared_mutex get_rw;
@@ -58,6 +61,10 @@ struct cmb200_engine {
 	uint64_t peer_size[GET_MAX_PEERS] = {};
 	std::atomic<uint64_t> small_get_requests{0}, small_get_hits{0}, small_get_launches{0};
 	unsigned long long *d_recoff_out = nullptr;  // arena offset per chunk of the current put slice (exchange records)
+	// k_get_small's sequence descriptors: one scratch region per CTA that can be resident (kernels.cu:gs_region_take)
+	uint4 *d_scratch = nullptr;
+	uint32_t *d_pool_bits = nullptr;
+	uint32_t pool_n = 0, region_entries = 0;
 	cudaEvent_t landed[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr};
 	TableView table{};
 	ArenaView arena{};
@@ -134,6 +141,7 @@ extern "C" void cmb200_engine_destroy(cmb200_engine *e) {
 	cudaSetDevice(e->device);
 	if (e->st) cudaStreamSynchronize(e->st);
 	if (e->copy) cudaStreamSynchronize(e->copy);
+	cudaFree(e->d_scratch); cudaFree(e->d_pool_bits); cudaFree(e->table.ckpt);
 	cudaFree(e->table.slots); cudaFree(e->table.fp); cudaFree(e->arena.base); cudaFree(e->arena.seg); cudaFree(e->d_counters);
 	cudaFree(e->d_pages[0]); cudaFree(e->d_pages[1]); cudaFree(e->d_stage);
 	cudaFree(e->d_addr); cudaFree(e->d_ts); cudaFree(e->d_valid); cudaFree(e->d_slot); cudaFree(e->d_vlen);
@@ -214,6 +222,21 @@ extern "C" cmb200_engine *cmb200_engine_create(const cmb200_config *cfg) {
 		if (e->flags & CMB200_FINGERPRINT) {
 			ENG_CHECK(cudaMalloc(&e->table.fp, (slots + 2) * 16));
 			ENG_CHECK(cudaMemsetAsync(e->table.fp, 0, (slots + 2) * 16, e->st));
+		}
+		if (get_small_supports(e->bsize)) {
+			// parse checkpoints per slot (64 bytes) and the descriptor scratch of the fused single-page get
+			const char *ck = getenv("CMB200_CKPT");
+			if (!ck || atoi(ck) != 0) {
+				ENG_CHECK(cudaMalloc(&e->table.ckpt, (slots + 2) * CKPT_WORDS * 4));
+				ENG_CHECK(cudaMemsetAsync(e->table.ckpt, 0, (slots + 2) * CKPT_WORDS * 4, e->st));
+			}
+			const int resident = get_small_residency(e->bsize);
+			if (resident <= 0) { set_error_msg("k_get_small does not fit this device"); goto fail; }
+			e->pool_n = (uint32_t)resident;
+			e->region_entries = get_small_region_entries(e->bsize);
+			ENG_CHECK(cudaMalloc(&e->d_scratch, (size_t)e->pool_n * e->region_entries * sizeof(uint4)));
+			ENG_CHECK(cudaMalloc(&e->d_pool_bits, ((size_t)e->pool_n + 31) / 32 * 4));
+			ENG_CHECK(cudaMemsetAsync(e->d_pool_bits, 0, ((size_t)e->pool_n + 31) / 32 * 4, e->st));
 		}
 		ENG_CHECK(cudaMalloc(&e->d_counters, 8 * sizeof(unsigned long long)));
 		ENG_CHECK(cudaMemsetAsync(e->d_counters, 0, 8 * sizeof(unsigned long long), e->st));
@@ -709,6 +732,7 @@ extern "C" int cmb200_get_small(cmb200_engine *e, size_t n, const cmb200_addr *a
 		job.out = (uint8_t *)pages_out + at * e->bsize;          // device memory or page-locked host memory (UVA)
 		job.status = ln->h_status;
 		for (int r = 0; r < GET_MAX_PEERS; r++) { job.peer[r] = e->peer_base[r]; job.peer_size[r] = e->peer_size[r]; }
+		job.scratch = e->d_scratch; job.region_entries = e->region_entries; job.pool_bits = e->d_pool_bits; job.pool_n = e->pool_n;
 		if (launch_get_small(job, ln->st)) return -1;
 		uint32_t done = 0;
 		for (uint64_t spins = 0; done < m;) {
@@ -1092,6 +1116,8 @@ extern "C" int cmb200_compact(cmb200_engine *e, uint64_t *reclaimed_out) {
 			CMB_CHECK(cudaMemsetAsync(fresh.slots, 0, (e->table.cap + 2) * sizeof(Slot), e->st));
 			if (fresh.fp) CMB_CHECK(cudaMemsetAsync(fresh.fp, 0, (e->table.cap + 2) * 16, e->st));
 			if (launch_rehash(e->table, fresh, e->st)) return -1;
+			// the slots have moved: their parse checkpoints are dropped (those records are walked by one warp)
+			if (e->table.ckpt) CMB_CHECK(cudaMemsetAsync(e->table.ckpt, 0, (e->table.cap + 2) * CKPT_WORDS * 4, e->st));
 			CMB_CHECK(cudaMemsetAsync(e->d_counters + 1, 0, sizeof(unsigned long long), e->st));   // tombstones
 			CMB_CHECK(cudaStreamSynchronize(e->st));
 			cudaFree(e->table.slots); cudaFree(e->table.fp);

@@ -15,6 +15,7 @@
 #include "lz4_encode_groups.cuh"
 #include <type_traits>
 #include "lz4_decode.cuh"
+#include "lz4_decode_cta.cuh"
 #include "streamgen.cuh"
 
 namespace cmb {
@@ -246,6 +247,8 @@ __global__ void __launch_bounds__(256) k_sample_scan(TableView t, const unsigned
 // own prefix and only the location from the slot (k_get_small).
 __device__ __forceinline__ void slot_publish(const EncodeJob &job, Slot &s, uint32_t i, uint32_t idx, unsigned long long off,
     uint32_t need, uint32_t clen, unsigned long long au, unsigned long long al, uint64_t fp_hi, uint64_t fp_lo) {
+	// whatever checkpoints the slot has describe the record it is leaving (ckpt_store renews them)
+	if (job.table.ckpt) *reinterpret_cast<volatile uint32_t *>(&job.table.ckpt[(size_t)idx * CKPT_WORDS]) = 0u;
 	if (s.owner) { atomicAdd(job.table.remote, (unsigned long long)-1ll); s.owner = 0; }   // now newest here (alloc held the remote length)
 	else if (s.alloc) atomicAdd(job.arena.garbage, (unsigned long long)s.alloc);         // the record this one replaces
 	s.addr_u = au; s.addr_l = al;
@@ -259,9 +262,23 @@ __device__ __forceinline__ void slot_publish(const EncodeJob &job, Slot &s, uint
 	if (job.rec_out) job.rec_out[i] = off;
 }
 
+// Parse checkpoints of the record just published in slot idx (whole warp; lane k holds word k, see
+// lz4_encode_lean).  slot_publish has zeroed the tag and fenced; the words go in, then the tag that
+// names this record version — a reader takes the words only between two equal reads of that tag.
+__device__ __forceinline__ void ckpt_store(const EncodeJob &job, uint32_t idx, unsigned long long off, uint32_t clen,
+    uint32_t ck, int lane) {
+	if (!job.table.ckpt) return;
+	uint32_t *w = job.table.ckpt + (size_t)idx * CKPT_WORDS;
+	__syncwarp();
+	if (lane >= 1 && lane < (int)CKPT_WORDS) *reinterpret_cast<volatile uint32_t *>(w + lane) = ck;
+	__threadfence();
+	__syncwarp();
+	if (lane == 0) *reinterpret_cast<volatile uint32_t *>(w) = ckpt_tag(off, clen);
+}
+
 // Stores the finished block as a filemap record {data_prefix, block} (filemap.c:140-147) and
 // publishes it in the key table.  Called by the whole warp; lane 0 owns the bookkeeping.
-__device__ void commit_record(const EncodeJob &job, uint32_t i, uint32_t idx, const uint8_t *payload,
+__device__ unsigned long long commit_record(const EncodeJob &job, uint32_t i, uint32_t idx, const uint8_t *payload,
     uint32_t plen, int32_t clen, bool payload_ro, uint64_t fp_hi, uint64_t fp_lo, int lane) {
 	Slot &s = job.table.slots[idx];
 	const uint32_t need = (24u + plen + 15u) & ~15u;
@@ -285,7 +302,7 @@ __device__ void commit_record(const EncodeJob &job, uint32_t i, uint32_t idx, co
 		}
 	}
 	ok = __shfl_sync(CMB_FULL, ok, 0);
-	if (!ok) { if (lane == 0 && job.rec_out) job.rec_out[i] = ~0ull; return; }
+	if (!ok) { if (lane == 0 && job.rec_out) job.rec_out[i] = ~0ull; return ~0ull; }
 	off = __shfl_sync(CMB_FULL, off, 0);
 	uint8_t *rec = job.arena.base + off;
 	const unsigned long long au = job.addr[2 * i], al = job.addr[2 * i + 1];
@@ -306,6 +323,7 @@ __device__ void commit_record(const EncodeJob &job, uint32_t i, uint32_t idx, co
 	__threadfence();                                 // the record is complete before the slot points to it
 	__syncwarp();
 	if (lane == 0) slot_publish(job, s, i, idx, off, need, (uint32_t)clen, au, al, fp_hi, fp_lo);
+	return off;                                      // arena offset of the record (~0: dropped)
 }
 
 // Direct variant of commit_record: the block already sits in the arena at `base + 24` (this warp's
@@ -396,14 +414,14 @@ __global__ void __launch_bounds__(ENC == 1 ? ENC_RING_WARPS * 32 : ENC_PLAIN_WAR
 			base = __shfl_sync(CMB_FULL, base, 0);
 			if (in_arena) dst = job.arena.base + base + 24;
 		}
-		uint32_t clen;
+		uint32_t clen, ck = 0xffffffffu;
 		if (job.fps) {                  // fingerprint along the parse frontier: the page is read once
 			if (ENC == 2) clen = lz4_encode_warp<WIDE, true, FPNA>(src, job.nbytes, dst, job.accel, wsm, lane, fp_hi, fp_lo);
-			else clen = lz4_encode_lean<WIDE, true, FPNA, ENC == 1>(src, job.nbytes, dst, job.accel, wsm, ring, lane, fp_hi, fp_lo);
+			else clen = lz4_encode_lean<WIDE, true, FPNA, ENC == 1>(src, job.nbytes, dst, job.accel, wsm, ring, lane, fp_hi, fp_lo, ck);
 			if (lane == 0) { job.fps[2 * (size_t)i] = fp_hi; job.fps[2 * (size_t)i + 1] = fp_lo; }
 		} else {
 			if (ENC == 2) clen = lz4_encode_warp<WIDE, false, false>(src, job.nbytes, dst, job.accel, wsm, lane, fp_hi, fp_lo);
-			else clen = lz4_encode_lean<WIDE, false, false, ENC == 1>(src, job.nbytes, dst, job.accel, wsm, ring, lane, fp_hi, fp_lo);
+			else clen = lz4_encode_lean<WIDE, false, false, ENC == 1>(src, job.nbytes, dst, job.accel, wsm, ring, lane, fp_hi, fp_lo, ck);
 		}
 		if (lane == 0) job.lens[i] = (int32_t)clen;
 		if (store) {
@@ -411,8 +429,10 @@ __global__ void __launch_bounds__(ENC == 1 ? ENC_RING_WARPS * 32 : ENC_PLAIN_WAR
 			if (in_arena) {
 				const uint32_t used = commit_direct(job, i, idx, base, clen, fp_hi, fp_lo, lane);
 				if (lane == 0) seg_cur += used;
+				if (ENC != 2) ckpt_store(job, idx, base, clen, ck, lane);
 			} else {
-				commit_record(job, i, idx, dst, clen, (int32_t)clen, false, fp_hi, fp_lo, lane);
+				const unsigned long long at = commit_record(job, i, idx, dst, clen, (int32_t)clen, false, fp_hi, fp_lo, lane);
+				if (ENC != 2 && at != ~0ull) ckpt_store(job, idx, at, clen, ck, lane);
 			}
 		}
 	}
@@ -748,9 +768,9 @@ int launch_decode(const DecodeJob &job, cudaStream_t st) {
 // fused small-batch get: lookup + record staging (TMA) + decode in shared memory + page out
 // ------------------------------------------------------------------------------------------
 
-constexpr uint32_t GS_THREADS = 128;
-constexpr uint32_t GS_CTRL = 128 + 1152;          // control block + decode pipeline ring at the start of the shared memory
-static_assert(sizeof(DecodePipe) <= 1152, "decode pipe fits its slot");
+constexpr uint32_t GS_THREADS = DC_THREADS;       // 16 warps: one per parse section (lz4_decode_cta.cuh)
+constexpr uint32_t GS_CTRL = 128 + 1152;          // control block + decoder state at the start of the shared memory
+static_assert(sizeof(DecodeCta) <= 1152, "decoder state fits its slot");
 constexpr uint32_t GS_MAX_PAGE = 65536;           // record buffer + page buffer must fit 227 KiB
 struct GetShared {
 	unsigned long long bar;                   // mbarrier of the record copy
@@ -758,10 +778,16 @@ struct GetShared {
 	int32_t st;
 	uint32_t clen;                            // expected compressed_length (0 = raw page)
 	uint32_t owner;                           // rank + 1 when the record is in a peer's arena
-	int32_t used;
+	uint32_t idx;                             // slot of the key
+	uint32_t region;                          // scratch region this CTA holds (~0: none)
+	uint32_t sections;                        // 1 = one warp walks the block, 16 = the record's checkpoints are used
+	uint32_t ck[CKPT_WORDS];
 };
+static_assert(sizeof(GetShared) <= 128, "control block");
 __host__ __device__ inline uint32_t gs_recbuf(uint32_t nbytes) { return (24u + nbytes + 1024u + 31u) & ~15u; }
 bool get_small_supports(uint32_t nbytes) { return nbytes >= 64u && nbytes <= GS_MAX_PAGE && (nbytes & 15u) == 0; }
+size_t get_small_smem(uint32_t nbytes) { return GS_CTRL + gs_recbuf(nbytes) + nbytes; }
+uint32_t get_small_region_entries(uint32_t nbytes) { return dc_region(nbytes); }
 
 __device__ __forceinline__ unsigned long long ldv64(const unsigned long long *p) { return *reinterpret_cast<const volatile unsigned long long *>(p); }
 __device__ __forceinline__ uint32_t ldv32(const uint32_t *p) { return *reinterpret_cast<const volatile uint32_t *>(p); }
@@ -791,22 +817,92 @@ __device__ void gs_lookup(const GetJob &job, unsigned long long u, unsigned long
 			}
 		}
 	}
-	sh->st = st; sh->clen = clen; sh->off = off; sh->owner = owner;
+	sh->st = st; sh->clen = clen; sh->off = off; sh->owner = owner; sh->idx = idx;
+}
+
+// Scratch regions for the sequence descriptors: one per resident CTA, handed out through a bitmap
+// (the pool has as many regions as CTAs of this kernel can be resident, so a free one exists).
+__device__ uint32_t gs_region_take(const GetJob &job) {
+	uint32_t smid;
+	asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+	const uint32_t words = (job.pool_n + 31u) / 32u;
+	for (uint32_t probe = 0; probe < (1u << 22); probe++) {
+		const uint32_t w = (smid + probe) % words;
+		const uint32_t live = w + 1u == words && (job.pool_n & 31u) ? (1u << (job.pool_n & 31u)) - 1u : 0xffffffffu;
+		const uint32_t vacant = ~ldv32(&job.pool_bits[w]) & live;
+		if (!vacant) continue;
+		const uint32_t b = (uint32_t)__ffs(vacant) - 1u;
+		if (!((atomicOr(&job.pool_bits[w], 1u << b) >> b) & 1u)) return w * 32u + b;
+	}
+	return 0xffffffffu;
+}
+__device__ void gs_region_give(const GetJob &job, uint32_t r) { atomicAnd(&job.pool_bits[r / 32u], ~(1u << (r & 31u))); }
+
+// The record's checkpoints (ckpt_store) -> section table.  Seqlock: tag, words, tag again; the tag
+// names the record (arena offset + length), so words of another record version never pass.
+__device__ void gs_sections(const GetJob &job, GetShared *sh, DecodeCta *dc, uint32_t clen, bool local) {
+	const uint32_t n = job.nbytes, S = n / DC_CHAINS;
+	bool use = false;
+	if (local && job.table.ckpt && CMB_GET_CKPT) {
+		const uint32_t *ck = job.table.ckpt + (size_t)sh->idx * CKPT_WORDS;
+		const uint32_t want = ckpt_tag(sh->off, clen);
+		if (ldv32(ck) == want) {
+			__threadfence();
+			for (uint32_t k = 1; k < CKPT_WORDS; k++) sh->ck[k] = ldv32(ck + k);
+			__threadfence();
+			use = ldv32(ck) == want;
+		}
+	}
+	for (uint32_t c = 0; c < DC_CHAINS; c++) { dc->ip0[c] = 0xffffffffu; dc->op0[c] = 0; dc->op_end[c] = 0; dc->cnt[c] = 0; dc->ip1[c] = 0; dc->op1[c] = 0; }
+	dc->err = 0;
+	dc->ip0[0] = 0; dc->op0[0] = 0;
+	uint32_t prev = 0;
+	if (use) {
+		for (uint32_t k = 1; k < DC_CHAINS; k++) {
+			const uint32_t v = sh->ck[k];
+			if (v == 0xffffffffu) continue;                      // no sequence starts in this section
+			const uint32_t ip = v >> CKPT_POS_BITS, op = k * S + (v & ((1u << CKPT_POS_BITS) - 1u));
+			if (ip >= clen || op >= n || op >= (k + 1u) * S || ip <= dc->ip0[prev]) { use = false; break; }
+			dc->ip0[k] = ip; dc->op0[k] = op;
+			dc->op_end[prev] = op;
+			prev = k;
+		}
+	}
+	if (!use) {
+		for (uint32_t c = 1; c < DC_CHAINS; c++) dc->ip0[c] = 0xffffffffu;
+		prev = 0;
+	}
+	dc->op_end[prev] = n;
+	sh->sections = use ? DC_CHAINS : 1u;
+}
+
+// Do the sections add up to the serial parse?  (one thread)
+__device__ bool gs_sections_fit(const DecodeCta *dc, uint32_t clen, uint32_t n) {
+	if (dc->err) return false;
+	uint32_t prev = 0;
+	for (uint32_t c = 1; c < DC_CHAINS; c++) {
+		if (dc->ip0[c] == 0xffffffffu) continue;
+		if (dc->ip1[prev] != dc->ip0[c] || dc->op1[prev] != dc->op0[c]) return false;
+		prev = c;
+	}
+	return dc->ip1[prev] == clen && dc->op1[prev] == n;          // filemap.c:244-248: consumed == compressed_length
 }
 
 __global__ void __launch_bounds__(GS_THREADS, 1) k_get_small(GetJob job) {
 	extern __shared__ __align__(128) uint8_t smem[];
 	GetShared *sh = reinterpret_cast<GetShared *>(smem);
-	DecodePipe *dp = reinterpret_cast<DecodePipe *>(smem + 128);
+	DecodeCta *dc = reinterpret_cast<DecodeCta *>(smem + 128);
 	uint8_t *rec = smem + GS_CTRL;
 	uint8_t *page = rec + gs_recbuf(job.nbytes);
 	const uint32_t i = blockIdx.x, tid = threadIdx.x;
 	const int lane = tid & 31;
+	const uint32_t warp = tid >> 5;
 	const unsigned long long u = job.addr[2 * (size_t)i], l = job.addr[2 * (size_t)i + 1];
 	uint8_t *out = job.out + (size_t)i * job.nbytes;
 	const uint32_t s_bar = smem_addr(&sh->bar);
 	if (job.valid && !job.valid[i]) { if (tid == 0) job.status[i] = ST_INVALID; return; }
 	if (tid == 0) {
+		sh->region = 0xffffffffu;
 		mbar_init(s_bar, 1u);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -863,15 +959,35 @@ __global__ void __launch_bounds__(GS_THREADS, 1) k_get_small(GetJob job) {
 			result = ST_HIT;
 			break;
 		}
-		// three-stage pipeline over the token chain (lz4_decode.cuh): parser, literal copies, match copies
-		if (tid == 0) { dp->parsed = 0; dp->lit_done = 0; dp->mat_done = 0; dp->result = 0; dp->abort = 0; dp->lit_by[0] = dp->lit_by[1] = 0; dp->lit_ended = 0; }
+		// ---- LZ4 block -> page, both in shared memory (lz4_decode_cta.cuh) ----
+		if (tid == 0) {
+			if (sh->region == 0xffffffffu) sh->region = gs_region_take(job);
+			gs_sections(job, sh, dc, clen, st == ST_HIT);
+		}
 		__syncthreads();
-		if (tid < 32) lz4_pipe_parse(smem_addr(dp), smem_addr(rec + 24), clen, job.nbytes, lane);
-		else if (tid < 64) lz4_pipe_literals(smem_addr(dp), smem_addr(rec + 24), smem_addr(page), rec + 24, page, 0u, lane);
-		else if (tid < 96) lz4_pipe_matches(smem_addr(dp), smem_addr(page), lane);
-		else lz4_pipe_literals(smem_addr(dp), smem_addr(rec + 24), smem_addr(page), rec + 24, page, 1u, lane);
+		if (sh->region == 0xffffffffu) { result = ST_BAD_DECODE; break; }           // cannot happen with a pool sized to residency
+		uint4 *desc = job.scratch + (size_t)sh->region * job.region_entries;
+		const uint32_t stride = dc_stride(job.nbytes);
+		const uint32_t blk_s = smem_addr(rec + 24), page_s = smem_addr(page);
+		bool good = false;
+		for (int pass = 0; pass < 2 && !good; pass++) {
+			const bool many = sh->sections > 1u;
+			if (dc->ip0[warp] != 0xffffffffu)
+				dc_parse_chain(dc, warp, blk_s, clen, job.nbytes, desc + (size_t)warp * stride,
+				    many ? stride : job.region_entries, lane);
+			__syncthreads();
+			good = gs_sections_fit(dc, clen, job.nbytes);
+			if (good || !many) break;
+			// checkpoints that do not describe this block (never seen; the record is what counts): one walk
+			__syncthreads();
+			if (tid == 0) gs_sections(job, sh, dc, clen, false);
+			__syncthreads();
+		}
+		if (!good) { result = ST_BAD_DECODE; break; }             // filemap.c:244-248
+		dc_literals(dc, desc, stride, blk_s, page_s, rec + 24, page, warp, lane);
 		__syncthreads();
-		if (dp->result != (int32_t)clen || dp->abort) { result = ST_BAD_DECODE; break; }     // filemap.c:244-248
+		if (warp == 0) dc_matches(dc, desc, stride, page_s, lane);
+		__syncthreads();
 		for (uint32_t k = tid; k < job.nbytes / 16u; k += GS_THREADS)
 			reinterpret_cast<uint4 *>(out)[k] = reinterpret_cast<const uint4 *>(page)[k];
 		__threadfence_system();                           // `out` may be host memory that is read as soon as the status flips
@@ -880,12 +996,16 @@ __global__ void __launch_bounds__(GS_THREADS, 1) k_get_small(GetJob job) {
 	}
 	// status may live in page-locked host memory that the caller polls: the page first, then the status
 	__syncthreads();
-	if (tid == 0) { __threadfence_system(); *reinterpret_cast<volatile int32_t *>(&job.status[i]) = result; }
+	if (tid == 0) {
+		if (sh->region != 0xffffffffu) gs_region_give(job, sh->region);
+		__threadfence_system();
+		*reinterpret_cast<volatile int32_t *>(&job.status[i]) = result;
+	}
 }
 
 int launch_get_small(const GetJob &job, cudaStream_t st) {
 	if (job.n == 0) return 0;
-	const size_t smem = GS_CTRL + gs_recbuf(job.nbytes) + job.nbytes;
+	const size_t smem = get_small_smem(job.nbytes);
 	static size_t configured = 0;
 	if (smem > configured) {
 		CMB_CHECK(cudaFuncSetAttribute(k_get_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -894,6 +1014,15 @@ int launch_get_small(const GetJob &job, cudaStream_t st) {
 	k_get_small<<<job.n, GS_THREADS, smem, st>>>(job);
 	CMB_CHECK(cudaGetLastError());
 	return 0;
+}
+
+// CTAs of k_get_small that can be resident on the device at once (= scratch regions needed)
+int get_small_residency(uint32_t nbytes) {
+	const size_t smem = get_small_smem(nbytes);
+	if (cudaFuncSetAttribute(k_get_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+	int per_sm = 0;
+	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_get_small, (int)GS_THREADS, smem) != cudaSuccess) return -1;
+	return per_sm * sm_count();
 }
 
 // ------------------------------------------------------------------------------------------

@@ -31,7 +31,21 @@ struct TableView {
 	unsigned long long *tombs;   // deleted main-table slots (rebuild trigger)
 	unsigned long long *remote;  // keys whose newest record lives on another GPU
 	uint64_t *fp;                // optional, 2 x u64 per slot {hi, lo}
+	uint32_t *ckpt;              // optional, CKPT_WORDS per slot: parse checkpoints of the slot's record
 };
+
+// Parse checkpoints (lz4_decode_cta.cuh): word 0 = tag naming the record version (0 = none), word k
+// (1..15) = where the first LZ4 sequence at or after k/16 of the page starts:
+// block offset << CKPT_POS_BITS | (output position - k * n/16), or ~0 when no sequence starts in
+// that sixteenth.  Written by the encoder (kernels.cu:ckpt_store), read by k_get_small.
+constexpr uint32_t CKPT_WORDS = 16;
+constexpr uint32_t CKPT_POS_BITS = 13;       // n/16 <= 8192 for pages up to 128 KiB
+#ifndef CMB_GET_CKPT
+#define CMB_GET_CKPT 1
+#endif
+__host__ __device__ inline uint32_t ckpt_tag(unsigned long long rec_off, uint32_t clen) {
+	return 0x80000000u | (((uint32_t)(rec_off >> 4) ^ (clen * 0x9E3779B1u)) & 0x7fffffffu);
+}
 
 #define ARENA_SEG_SLOTS 4096u    // resident encoder warps that can own an arena segment
 
@@ -115,8 +129,15 @@ struct GetJob {
 	int32_t *status;                  // n
 	const uint8_t *peer[GET_MAX_PEERS];
 	uint64_t peer_size[GET_MAX_PEERS];
+	uint4 *scratch;                   // pool_n regions of region_entries sequence descriptors (16 bytes each)
+	uint32_t region_entries;
+	uint32_t *pool_bits;              // bitmap of the regions in use
+	uint32_t pool_n;
 };
 bool get_small_supports(uint32_t nbytes);
+size_t get_small_smem(uint32_t nbytes);
+uint32_t get_small_region_entries(uint32_t nbytes);
+int get_small_residency(uint32_t nbytes);   // CTAs resident on the device at once, < 0 on error
 int launch_get_small(const GetJob &job, cudaStream_t st);
 
 int launch_fingerprint(const uint8_t *pages, uint64_t stride, uint32_t nbytes, uint32_t n,

@@ -28,6 +28,7 @@
 // accelerations use the plain kernel.
 #pragma once
 #include "lz4_encode.cuh"
+#include "kernels.h"
 
 namespace cmb {
 
@@ -170,11 +171,17 @@ __device__ __forceinline__ Lz4Around ring_around(const uint8_t *ring, uint32_t p
 // the ring — hangs off ONE comparison of the anchor with the position of the next such event.
 template <bool WIDE, bool FP, bool FP_NOALLOC, bool RING>
 __device__ uint32_t lz4_encode_lean(const uint8_t *__restrict__ src, uint32_t n, uint8_t *__restrict__ dst,
-    uint32_t accel, uint8_t *tab_smem, PageRing &ring, int lane, uint64_t &fp_hi, uint64_t &fp_lo) {
+    uint32_t accel, uint8_t *tab_smem, PageRing &ring, int lane, uint64_t &fp_hi, uint64_t &fp_lo, uint32_t &ck) {
 	Lz4Table<WIDE> tab;
 	tab.t = reinterpret_cast<decltype(tab.t)>(tab_smem);
 	const uint32_t lim4 = (n + 3u) & ~3u;
 	uint32_t op = 0, anchor = 0;
+	// Parse checkpoints for the CTA decoder (lz4_decode_cta.cuh): lane k (1..15) keeps where the first
+	// sequence at or after k * n/16 starts — block offset << CKPT_POS_BITS | distance past that
+	// position — or ~0 if none starts inside that sixteenth.  ck_at = the position the next one waits for.
+	const uint32_t ck_span = n / CKPT_WORDS;
+	uint32_t ck_k = 1, ck_at = ck_span ? ck_span : 0xffffffffu;
+	ck = 0xffffffffu;
 	EfFrontierT<FP_NOALLOC> fp;
 	if (FP) fp.start(src, n, lane);
 
@@ -222,9 +229,17 @@ __device__ uint32_t lz4_encode_lean(const uint8_t *__restrict__ src, uint32_t n,
 #define CMB_LZ4_NARROW_HIT 12
 #endif
 		uint32_t width = 32u, calm = 0u;                                    // lanes per batch; batches in a row that hit below lane 12
-		uint32_t next_event = 0;                                           // anchor at which the frontiers move next
+		uint32_t next_event = 0, ring_next = 0;                            // anchor at which the frontiers move next / a checkpoint is due
 		for (;;) {
 			if (anchor >= next_event) {
+				// a sequence starts at or after the next checkpoint position: this is the one to note
+				while (anchor >= ck_at) {
+					const uint32_t rel = anchor - ck_at;
+					if ((uint32_t)lane == ck_k) ck = rel < ck_span ? (op << CKPT_POS_BITS) | rel : 0xffffffffu;
+					ck_k++;
+					ck_at = ck_k < CKPT_WORDS ? ck_at + ck_span : 0xffffffffu;
+				}
+				if (anchor >= ring_next) {
 				// every 256 bytes: ring buffers, then fingerprint stripes up to the probes (in this order:
 				// the ring's out-of-line path would otherwise wait for the stripe the fingerprint prefetches)
 				if (RING) {
@@ -247,11 +262,13 @@ __device__ uint32_t lz4_encode_lean(const uint8_t *__restrict__ src, uint32_t n,
 					} else {
 						ring_step(ring, src, n, nbufs, g_lo, lane);
 					}
-					next_event = (g_lo + 1u) * RING_BUF + 4u;
+					ring_next = (g_lo + 1u) * RING_BUF + 4u;
 				} else {
-					next_event = (anchor | 255u) + 1u;
+					ring_next = (anchor | 255u) + 1u;
 				}
 				if (FP) fp.upto(src, anchor + 512u, lane);
+				}
+				next_event = min(ring_next, ck_at);
 			}
 			const bool en = anchor < en_below && (uint32_t)lane < width;
 			const uint32_t pos = en ? anchor + delta2 : 0u;        // disabled lanes read (and ignore) position 0 / ring offset 0
@@ -365,6 +382,14 @@ __device__ uint32_t lz4_encode_lean(const uint8_t *__restrict__ src, uint32_t n,
 			if (end > mflimit) break;                     // lz4.c:688
 		}
 		if (RING) ring_drain(ring);
+	}
+
+	// the last literals are a sequence start like any other
+	while (ck_k < CKPT_WORDS && ck_span) {
+		const uint32_t rel = anchor - ck_at;
+		if ((uint32_t)lane == ck_k) ck = (anchor >= ck_at && rel < ck_span) ? (op << CKPT_POS_BITS) | rel : 0xffffffffu;
+		ck_k++;
+		ck_at += ck_span;
 	}
 
 	// ---- last literals (lz4.c:713-729) ----

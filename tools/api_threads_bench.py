@@ -53,12 +53,15 @@ def run(lib, cm, pages, threads, per_thread, do_get):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--per-thread", type=int, default=256)
+    ap.add_argument("--threads", default="1,8,32,64")
+    ap.add_argument("--no-ref", action="store_true")
     a = ap.parse_args()
     pages = [E.gen_chunk_host(42, c, CH) for c in range(64)]
     os.environ.setdefault("CMB200_ARENA_MB", "8192")
     L = E.lib()
     out = {}
-    for threads in (1, 8, 32, 64):
+    tlist = [int(x) for x in a.threads.split(',')]
+    for threads in tlist:
         with tempfile.TemporaryDirectory() as d:
             cm = L.cachemap_create(d.encode(), 1 << 16, 12, 16)
             L.cachemap_put(cm, 1 << 40, 1, 0, pages[0].ctypes.data)      # engine start outside the clock
@@ -69,8 +72,8 @@ def main():
         print(threads, out[f"ours_T{threads}"], flush=True)
     from oracle import ef_oracle as O
     R = O.ref()
-    if R is not None:
-        for threads in (1, 8, 32, 64):
+    if R is not None and not a.no_ref:
+        for threads in tlist:
             with tempfile.TemporaryDirectory(dir="/dev/shm") as d:
                 cm = R.cachemap_create(d.encode(), 1 << 16, 12, 16)
                 put = run(R, cm, pages, threads, a.per_thread, False)
