@@ -8,5 +8,5 @@ anything itself and raises if the library or a CUDA device is missing — there 
 from .binding import (  # noqa: F401
     Cachemap, Engine, lib, library_path, compose_keys, lz4_encode_batch, lz4_decode_batch,
     fingerprint_batch, gen_chunk_host, gen_stream_ids, gen_addr, device_count, last_error,
-    HIT, MISS, INVALID, BAD_ENTRY, BAD_DECODE, REMOTE, FINGERPRINT, EXPORTED_SYMBOLS,
+    HIT, MISS, INVALID, BAD_ENTRY, BAD_DECODE, REMOTE, FINGERPRINT, EXPORTED_SYMBOLS, engine_stats,
 )

@@ -32,7 +32,7 @@ EXPORTED_SYMBOLS = [
     "cmb200_read_fingerprints", "cmb200_get_stats", "cmb200_compose_keys",
     "cmb200_set_stream_order", "cmb200_import_remote", "cmb200_locate_batch", "cmb200_save", "cmb200_load",
     "cmb200_put_step", "cmb200_import_records_dev", "cmb200_compact",
-    "cmb200_get_small", "cmb200_arena_ipc_handle", "cmb200_open_peer", "cmb200_close_peers",
+    "cmb200_get_small", "cmb200_get_small_begin", "cmb200_get_small_end", "cmb200_arena_ipc_handle", "cmb200_open_peer", "cmb200_close_peers",
     "cmb200_lz4_encode_batch", "cmb200_lz4_decode_batch", "cmb200_fingerprint_batch", "cmb200_fingerprint_dev",
     "cmb200_gen_chunk_host", "cmb200_gen_chunks_dev", "cmb200_gen_stream_ids", "cmb200_gen_addr",
 ]
@@ -124,6 +124,8 @@ def lib() -> C.CDLL:
         "cmb200_set_stream_order": (i32, [vp, u64, u64]),
         "cmb200_import_remote": (i32, [vp, sz, vp, vp, vp, vp, i32]),
         "cmb200_get_small": (i32, [vp, sz, vp, vp, vp]),
+        "cmb200_get_small_begin": (i32, [vp, sz, vp, vp, vp]),
+        "cmb200_get_small_end": (i32, [vp, vp, vp]),
         "cmb200_arena_ipc_handle": (i32, [vp, vp, vp]),
         "cmb200_open_peer": (i32, [vp, C.c_uint32, vp, C.c_uint64]),
         "cmb200_close_peers": (i32, [vp]),
@@ -258,6 +260,13 @@ def gen_addr(seed: int, cids, pshift: int):
 
 
 # ---- engine -------------------------------------------------------------------------------------
+
+def engine_stats(handle) -> dict:
+    """cmb200_get_stats of an engine handle (Engine.h, or cachemap_engine(cm) of the drop-in)."""
+    st = Stats()
+    _check(lib().cmb200_get_stats(handle, C.byref(st)), "cmb200_get_stats")
+    return {n: int(getattr(st, n)) for n, _ in Stats._fields_}
+
 
 class Engine:
     """cmb200_engine: the filemap-level batch API (addresses are (u, l) pairs)."""
@@ -449,9 +458,7 @@ class Engine:
         return fps
 
     def stats(self) -> dict:
-        s = Stats()
-        _check(lib().cmb200_get_stats(self.h, C.byref(s)), "cmb200_get_stats")
-        return {n: int(getattr(s, n)) for n, _ in Stats._fields_}
+        return engine_stats(self.h)
 
     def stream(self) -> int:
         return int(lib().cmb200_stream(self.h) or 0)

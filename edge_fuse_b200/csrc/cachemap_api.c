@@ -27,6 +27,8 @@
 #include <string.h>
 #include <sys/stat.h>
 #include <time.h>
+#include <sched.h>
+#include <semaphore.h>
 #include <unistd.h>
 
 #include "../../include/cachemap.h"
@@ -34,10 +36,12 @@
 
 #define COMBINE_MAX 32          /* get/unset requests one leader takes per GPU batch */
 #ifndef LEADERS
-#define LEADERS 16
-#endif                          /* batches of gets that may be in flight at once (each on its own engine lane):
-                                 * a get's latency is one chunk's decode, so requests are combined only when more
-                                 * than LEADERS callers are waiting; a B200 decodes 148 pages at a time */
+#define LEADERS 32
+#endif                          /* batches of gets that may be in flight at once, each on its own engine lane
+                                 * (<= the engine's CMB_GET_LANES); see the combining queue below */
+#ifndef GET_CALLERS
+#define GET_CALLERS 32          /* callers inside the combining queue at once; the rest sleep at its door */
+#endif
 #define FLUSH_MAX 1024          /* pages the flusher hands over per GPU batch */
 #define PNUM_SHIFT 44           /* cachemap.c:155 */
 
@@ -49,10 +53,9 @@ struct fm_req {
 	cmb200_addr addr;
 	void *out;              /* REQ_GET: malloc()ed page (or dst) on a hit, else NULL */
 	void *dst;              /* REQ_GET: caller's buffer to fill instead of malloc()ing one */
-	const uint8_t *staged;  /* REQ_GET hit: the page in the leader's stage buffer, copied out by the waiter itself */
-	int stage_buf;          /* which stage buffer `staged` points into */
+	const volatile int32_t *status; /* where this request's answer appears (set, under q_mu, when its batch is launched) */
+	int slot, pos;          /* leader slot of its batch and position in that batch's stage buffer */
 	int bad_entry;
-	int done;
 	struct fm_req *next;
 };
 
@@ -73,13 +76,18 @@ struct filemap {
 	pthread_mutex_t init_mu;
 	int init_state;         /* 0 = not yet, 1 = ready, -1 = failed */
 	cmb200_engine *eng;
-	uint8_t *h_stage;       /* page-locked, LEADERS x 2 x COMBINE_MAX pages (get results; two buffers alternate per leader slot) */
-	int stage_turn[LEADERS];        /* stage buffer of the slot's next batch */
-	int stage_readers[2 * LEADERS]; /* waiters still copying their page out of each buffer (under q_mu) */
-	int leader_busy[LEADERS];       /* a batch is being run in this slot (under q_mu) */
+	uint8_t *h_stage;       /* page-locked, LEADERS x COMBINE_MAX pages: the stage buffer of each leader slot */
+	int leader_busy[LEADERS];       /* a batch is in flight in this slot (under q_mu) */
+	int batch_left[LEADERS];        /* its requesters that have not taken their answer yet (atomic) */
+	cmb200_small_ticket ticket[LEADERS];    /* the slot's launch (lane < 0: the batch was answered synchronously) */
+	int32_t sync_status[LEADERS][COMBINE_MAX];      /* answers of a synchronously run batch */
+	int launching;                  /* a caller is inside a launch: arrivals meanwhile form the next batch (set under q_mu) */
+	sem_t q_door;                   /* GET_CALLERS permits: the queue is built on watching, not sleeping, and that only
+	                                 * works while the watchers have cores of their own */
+	int busy_slots;                 /* slots with a batch in flight (atomic; changes under q_mu) */
+	int q_len;                      /* requests queued and not yet launched (atomic; changes under q_mu) */
 	/* combining queue (gets, unsets) */
 	pthread_mutex_t q_mu;
-	pthread_cond_t q_cv;
 	struct fm_req *q_head, *q_tail;
 	/* write-behind ring: slots [wb_tail, wb_head) are in use, numbered modulo wb_n */
 	pthread_mutex_t wb_mu;
@@ -132,7 +140,7 @@ filemap_engine_ready(struct filemap *m)
 		cfg.flags = env_long("CMB200_FINGERPRINT", 0) ? CMB200_FINGERPRINT : 0;
 		m->eng = cmb200_engine_create(&cfg);
 		if (m->eng) {
-			m->h_stage = cmb200_host_alloc((size_t)2 * LEADERS * COMBINE_MAX * m->bsize);
+			m->h_stage = cmb200_host_alloc((size_t)LEADERS * COMBINE_MAX * m->bsize);
 			/* ring of ~64 MiB by default, at least 64 pages */
 			long slots = env_long("CMB200_WB_SLOTS", (64L << 20) / m->bsize);
 			if (slots > 0 && slots < 64)
@@ -193,7 +201,7 @@ filemap_create(char *destdir, uint64_t n, int compress_accel, int pshift)
 	strcpy(m->destdir, destdir);
 	pthread_mutex_init(&m->init_mu, NULL);
 	pthread_mutex_init(&m->q_mu, NULL);
-	pthread_cond_init(&m->q_cv, NULL);
+	sem_init(&m->q_door, 0, GET_CALLERS);
 	pthread_mutex_init(&m->wb_mu, NULL);
 	pthread_cond_init(&m->wb_space, NULL);
 	pthread_cond_init(&m->wb_work, NULL);
@@ -260,7 +268,7 @@ filemap_free(struct filemap *m)
 	pthread_mutex_destroy(&m->snap_mu);
 	pthread_mutex_destroy(&m->init_mu);
 	pthread_mutex_destroy(&m->q_mu);
-	pthread_cond_destroy(&m->q_cv);
+	sem_destroy(&m->q_door);
 	pthread_mutex_destroy(&m->wb_mu);
 	pthread_cond_destroy(&m->wb_space);
 	pthread_cond_destroy(&m->wb_work);
@@ -480,141 +488,180 @@ filemap_ring_lookup(struct filemap *m, const cmb200_addr *addr, void *dst)
 	return page;
 }
 
-/* Runs one combined batch of gets / unsets in leader slot `ls`.  Called by the leader without q_mu held. */
+/* Combining queue of the single-page calls (cachemap_get / filemap_unset from FUSE worker threads).
+ *
+ * A get's latency is one page's decode on one SM and a B200 decodes 148 pages at a time, so a
+ * request is launched at once when it can be: whoever finds a free leader slot and nobody else
+ * inside a launch takes everything queued (<= COMBINE_MAX) and launches it as ONE fused kernel
+ * (cmb200_get_small_begin).  Kernel launches are what limits the rate with many callers (~100 k
+ * launches/s whatever the number of threads), and only one caller launches at a time, so under load
+ * the requests that arrive during a launch ride together in the next one.
+ * Nobody waits for a batch: the kernel answers each request in its own status word (page-locked
+ * memory) and every requester watches ITS word, copies ITS page out of the slot's stage buffer and
+ * leaves; the last one out ends the launch (cmb200_get_small_end) and frees the slot.
+ */
+static const int32_t fm_answered = CMB200_MISS;         /* status word of requests that have no page to wait for */
+
+/* Takes up to COMBINE_MAX queued requests into leader slot `ls` and launches them.  Called with q_mu
+ * held and m->launching set; returns with q_mu held. */
 static void
-filemap_run_batch(struct filemap *m, struct fm_req **reqs, int count, int ls)
+filemap_lead(struct filemap *m, int ls)
 {
+	struct fm_req *batch[COMBINE_MAX];
 	cmb200_addr addr[COMBINE_MAX];
-	int32_t status[COMBINE_MAX];
 	int idx[COMBINE_MAX];
-	int k;
+	int nb = 0, k;
+
+	while (m->q_head && nb < COMBINE_MAX) {
+		batch[nb++] = m->q_head;
+		m->q_head = m->q_head->next;
+	}
+	if (!m->q_head)
+		m->q_tail = NULL;
+	__atomic_fetch_sub(&m->q_len, nb, __ATOMIC_RELAXED);
+	pthread_mutex_unlock(&m->q_mu);
 
 	k = 0;
-	for (int i = 0; i < count; i++)
-		if (reqs[i]->kind == REQ_UNSET)
-			addr[k++] = reqs[i]->addr;
+	for (int i = 0; i < nb; i++)
+		if (batch[i]->kind == REQ_UNSET)
+			addr[k++] = batch[i]->addr;
 	if (k)
-		cmb200_unset_batch(m->eng, (size_t)k, addr);
+		cmb200_unset_batch(m->eng, (size_t)k, addr);    /* unsets first: they change the table the gets read by key */
 
 	k = 0;
-	for (int i = 0; i < count; i++) {
-		if (reqs[i]->kind != REQ_GET)
+	for (int i = 0; i < nb; i++) {
+		if (batch[i]->kind != REQ_GET)
 			continue;
-		addr[k] = reqs[i]->addr;
+		addr[k] = batch[i]->addr;
 		idx[k] = i;
 		k++;
 	}
-	/* the fused small-batch get: one kernel on the get stream, pages land in a page-locked stage
-	 * buffer directly; page sizes it does not serve (> 64 KiB) take the two-kernel batch path.
-	 * The hits are NOT copied here: every waiter copies its own page out of the stage when it wakes
-	 * up (filemap_submit_many), so a batch of k pages costs the leader no k memcpys; the two stage
-	 * buffers alternate, and a buffer is reused only when its waiters are done with it. */
-	const int sb = 2 * ls + m->stage_turn[ls];
-	m->stage_turn[ls] ^= 1;
-	uint8_t *stage = m->h_stage + (size_t)sb * COMBINE_MAX * (size_t)m->bsize;
+	uint8_t *stage = m->h_stage + (size_t)ls * COMBINE_MAX * (size_t)m->bsize;
+	const volatile int32_t *answers = m->sync_status[ls];
+	m->ticket[ls].lane = -1;
 	if (k) {
-		pthread_mutex_lock(&m->q_mu);
-		while (m->stage_readers[sb] > 0)
-			pthread_cond_wait(&m->q_cv, &m->q_mu);
-		pthread_mutex_unlock(&m->q_mu);
-	}
-	int rc = k ? cmb200_get_small(m->eng, (size_t)k, addr, stage, status) : 0;
-	if (k && rc == -2)
-		rc = cmb200_get_batch(m->eng, (size_t)k, addr, NULL, stage, status);
-	if (k && rc == 0) {
-		for (int j = 0; j < k; j++) {
-			struct fm_req *r = reqs[idx[j]];
-			if (status[j] == CMB200_HIT) {
-				r->staged = stage + (size_t)j * m->bsize;
-				r->stage_buf = sb;
-			} else if (status[j] == CMB200_BAD_ENTRY) {
-				r->bad_entry = 1;
-			}
+		/* the fused small-batch get: one kernel on a stream of its own, pages land in the page-locked
+		 * stage buffer directly; page sizes it does not serve (> 64 KiB) take the two-kernel batch path,
+		 * synchronously */
+		int rc = cmb200_get_small_begin(m->eng, (size_t)k, addr, stage, &m->ticket[ls]);
+		if (rc == 0) {
+			answers = m->ticket[ls].status;
+		} else {
+			m->ticket[ls].lane = -1;
+			if (rc == -2)
+				rc = cmb200_get_batch(m->eng, (size_t)k, addr, NULL, stage, m->sync_status[ls]);
+			if (rc != 0)
+				for (int j = 0; j < k; j++)
+					m->sync_status[ls][j] = CMB200_MISS;
 		}
 	}
-}
 
-/* Queues `count` requests (an array) and returns when all of them have been served.  The queue is
- * FIFO and batches complete in order, so the last request finishing means all have. */
-/* Copies the pages of the caller's own finished requests out of the stage buffers and releases
- * them.  Called without q_mu. */
-static void
-filemap_copy_out(struct filemap *m, struct fm_req *reqs, int count)
-{
-	int released[2 * LEADERS] = { 0 }, any = 0;
-	for (int i = 0; i < count; i++) {
-		struct fm_req *r = &reqs[i];
-		if (!r->staged)
-			continue;
-		r->out = r->dst ? r->dst : malloc((size_t)m->bsize);    /* filemap.c:242 */
-		if (r->out)
-			memcpy(r->out, r->staged, (size_t)m->bsize);
-		released[r->stage_buf]++;
-		any = 1;
-		r->staged = NULL;
-	}
-	if (any) {
-		pthread_mutex_lock(&m->q_mu);
-		for (int b = 0; b < 2 * LEADERS; b++)
-			m->stage_readers[b] -= released[b];
-		pthread_cond_broadcast(&m->q_cv);
-		pthread_mutex_unlock(&m->q_mu);
+	pthread_mutex_lock(&m->q_mu);
+	__atomic_store_n(&m->batch_left[ls], nb, __ATOMIC_RELEASE);
+	for (int j = 0; j < k; j++)
+		batch[idx[j]]->pos = j;
+	k = 0;
+	for (int i = 0; i < nb; i++) {
+		/* slot and position first: the requester goes on as soon as it sees its status pointer, and
+		 * may be gone (its request with it) right after */
+		struct fm_req *r = batch[i];
+		r->slot = ls;
+		__atomic_store_n(&r->status, r->kind == REQ_GET ? answers + k++ : &fm_answered, __ATOMIC_RELEASE);
 	}
 }
 
+/* Queues `count` requests (an array) and returns when all of them have been answered.  A requester
+ * takes q_mu once to queue; after that it only takes it again to launch a batch itself or to sleep
+ * when every slot is busy — watching for its launch and for its answer needs no lock. */
 static void
 filemap_submit_many(struct filemap *m, struct fm_req *reqs, int count)
 {
 	for (int i = 0; i < count; i++) {
-		reqs[i].done = 0;
-		reqs[i].staged = NULL;
+		reqs[i].status = NULL;
+		reqs[i].slot = -1;
+		reqs[i].pos = 0;
 		reqs[i].next = i + 1 < count ? &reqs[i + 1] : NULL;
 	}
-	struct fm_req *req = &reqs[count - 1];
+	while (sem_wait(&m->q_door) != 0)
+		;
 	pthread_mutex_lock(&m->q_mu);
 	if (m->q_tail)
 		m->q_tail->next = &reqs[0];
 	else
 		m->q_head = &reqs[0];
-	m->q_tail = req;
-	while (!req->done) {
-		/* Up to LEADERS batches are in flight at once: while one batch's kernel runs, the callers that
-		 * arrived meanwhile form the next one instead of waiting for it.  Unsets stay alone (they
-		 * change the table the gets read by key). */
-		int ls = -1;
-		for (int k = 0; k < LEADERS; k++)
-			if (!m->leader_busy[k]) { ls = k; break; }
-		if (ls < 0 || !m->q_head) {
-			pthread_cond_wait(&m->q_cv, &m->q_mu);
-			continue;
-		}
-		struct fm_req *batch[COMBINE_MAX];
-		int nb = 0;
-		m->leader_busy[ls] = 1;
-		while (m->q_head && nb < COMBINE_MAX) {
-			batch[nb++] = m->q_head;
-			m->q_head = m->q_head->next;
-		}
-		if (!m->q_head)
-			m->q_tail = NULL;
-		pthread_mutex_unlock(&m->q_mu);
-		/* a long request chain spans several batches: take my pages of the earlier ones out first,
-		 * the batch I am about to run may need their stage buffer */
-		filemap_copy_out(m, reqs, count);
-		filemap_run_batch(m, batch, nb, ls);
-		pthread_mutex_lock(&m->q_mu);
-		for (int i = 0; i < nb; i++) {
-			if (batch[i]->staged)
-				m->stage_readers[batch[i]->stage_buf]++;
-			batch[i]->done = 1;
-		}
-		m->leader_busy[ls] = 0;
-		pthread_cond_broadcast(&m->q_cv);
-	}
+	m->q_tail = &reqs[count - 1];
+	__atomic_fetch_add(&m->q_len, count, __ATOMIC_RELAXED);
 	pthread_mutex_unlock(&m->q_mu);
-	/* every caller copies the pages of ITS requests out of the stage (in parallel with the other
-	 * callers and with the next batch's kernel), then releases the stage buffer */
-	filemap_copy_out(m, reqs, count);
+
+	for (int i = 0; i < count; i++) {
+		struct fm_req *r = &reqs[i];
+		const volatile int32_t *answer;
+		unsigned waited = 0;
+		while (!(answer = __atomic_load_n(&r->status, __ATOMIC_ACQUIRE))) {
+			/* Watch without the lock while somebody is inside a launch (microseconds: it either has this
+			 * request with it or leaves it to the next launch), while every slot is busy, and — for a
+			 * short while — when a launch now would carry very few requests into one of the last free
+			 * slots: with many callers the slots are what runs out, and batches of 1 use them up. */
+			const int busy = __atomic_load_n(&m->busy_slots, __ATOMIC_RELAXED);
+			if (__atomic_load_n(&m->launching, __ATOMIC_ACQUIRE) || busy >= LEADERS ||
+			    (busy >= LEADERS / 2 && waited < 256u && 4 * __atomic_load_n(&m->q_len, __ATOMIC_RELAXED) < busy)) {
+#if defined(__x86_64__)
+				__builtin_ia32_pause();
+#endif
+				if ((++waited & 1023u) == 0u)
+					sched_yield();
+				continue;
+			}
+			pthread_mutex_lock(&m->q_mu);
+			if (!r->status && !m->launching) {
+				int ls = -1;
+				for (int k = 0; k < LEADERS; k++)
+					if (!m->leader_busy[k]) { ls = k; break; }
+				if (ls >= 0) {
+					m->launching = 1;
+					m->leader_busy[ls] = 1;
+					__atomic_fetch_add(&m->busy_slots, 1, __ATOMIC_RELAXED);
+					filemap_lead(m, ls);                    /* (drops and retakes q_mu around the launch) */
+					__atomic_store_n(&m->launching, 0, __ATOMIC_RELEASE);
+				}
+			}
+			pthread_mutex_unlock(&m->q_mu);
+		}
+		const int ls = r->slot;
+
+		/* my answer: the kernel writes the page, fences, then the status word */
+		int32_t st;
+		for (unsigned spins = 0; (st = *answer) == CMB200_SMALL_PENDING; spins++) {
+#if defined(__x86_64__)
+			__builtin_ia32_pause();
+#endif
+			if ((spins & 4095u) == 4095u)
+				sched_yield();
+		}
+		__atomic_thread_fence(__ATOMIC_ACQUIRE);
+		if (r->kind == REQ_GET) {
+			if (st == CMB200_HIT) {
+				r->out = r->dst ? r->dst : malloc((size_t)m->bsize);    /* filemap.c:242 */
+				if (r->out)
+					memcpy(r->out, m->h_stage + ((size_t)ls * COMBINE_MAX + (size_t)r->pos) * (size_t)m->bsize,
+					    (size_t)m->bsize);
+			} else if (st == CMB200_BAD_ENTRY) {
+				r->bad_entry = 1;
+			}
+		}
+
+		if (__atomic_sub_fetch(&m->batch_left[ls], 1, __ATOMIC_ACQ_REL) == 0) {
+			/* last one out: every status word of the launch has been seen answered, so ending it does
+			 * not wait; then the slot and its stage buffer are free again */
+			if (m->ticket[ls].lane >= 0)
+				cmb200_get_small_end(m->eng, &m->ticket[ls], NULL);
+			pthread_mutex_lock(&m->q_mu);
+			m->leader_busy[ls] = 0;
+			__atomic_fetch_sub(&m->busy_slots, 1, __ATOMIC_RELEASE);
+			pthread_mutex_unlock(&m->q_mu);
+		}
+	}
+	sem_post(&m->q_door);
 }
 
 static void

@@ -12,6 +12,7 @@
 #include <atomic>
 #include <mutex>
 #include <shared_mutex>
+#include <sched.h>
 #include <string>
 #include <new>
 #include <stdio.h>
@@ -46,15 +47,39 @@ struct cmb200_engine {
 	// a put batch on `st` nor take `mu`
 	// Several small gets may be in flight at once (two leader threads of the combining queue, or any
 	// callers of cmb200_get_small): each takes one LANE — a stream plus page-locked request / status
-	// words — and the shared side of get_rw; what moves records or peer mappings (compaction, peers,
-	// destroy) takes get_rw exclusively.
+	// words — and the open side of get_gate; what moves records or peer mappings (compaction, peers,
+	// destroy) closes get_gate.
 #ifndef CMB_GET_LANES
-#define CMB_GET_LANES 16
+#define CMB_GET_LANES 32
 #endif
 	static constexpr int GET_LANES = CMB_GET_LANES;
-	struct GetLane { std::mutex mu; cudaStream_t st = nullptr; int32_t *h_status = nullptr; cmb200_addr *h_addr = nullptr; };
+	struct GetLane { std::atomic<int> busy{0}; cudaStream_t st = nullptr; int32_t *h_status = nullptr; cmb200_addr *h_addr = nullptr; };
 	GetLane lane[GET_LANES];
-	std::shared_mutex get_rw;
+	// A small get may be begun by one thread and ended by another (cmb200_get_small_begin / _end), so
+	// the "no small get in flight" condition is a counter and a closing flag, not a lock a thread owns.
+	struct GetGate {
+		std::atomic<int> active{0}, closed{0};
+		void enter() {
+			for (;;) {
+				while (closed.load(std::memory_order_acquire)) sched_yield();
+				active.fetch_add(1, std::memory_order_acq_rel);
+				if (!closed.load(std::memory_order_acquire)) return;
+				active.fetch_sub(1, std::memory_order_acq_rel);
+			}
+		}
+		void leave() { active.fetch_sub(1, std::memory_order_acq_rel); }
+		void close() {                        // exclusive: waits for the gets in flight, holds new ones off
+			int open = 0;
+			while (!closed.compare_exchange_weak(open, 1, std::memory_order_acq_rel)) { open = 0; sched_yield(); }
+			while (active.load(std::memory_order_acquire)) sched_yield();
+		}
+		void reopen() { closed.store(0, std::memory_order_release); }
+	} get_gate;
+	struct GateClosed {                           // scope guard of the exclusive side
+		GetGate &g;
+		explicit GateClosed(GetGate &gate) : g(gate) { g.close(); }
+		~GateClosed() { g.reopen(); }
+	};
 	std::atomic<uint32_t> lane_turn{0};
 	static constexpr size_t GET_SMALL_MAX = 1024;
 	const uint8_t *peer_base[GET_MAX_PEERS] = {};
@@ -700,68 +725,105 @@ extern "C" int cmb200_import_remote(cmb200_engine *e, size_t n, const cmb200_add
 
 // ---- small gets: one fused kernel on their own stream ------------------------------------------
 
-extern "C" int cmb200_get_small(cmb200_engine *e, size_t n, const cmb200_addr *addr, void *pages_out, int32_t *status_out) {
+// Begin / end halves of a small get.  begin launches the kernel on a free lane and returns at once;
+// the answers appear in t->status (page-locked host memory the kernel writes: a page, a system-wide
+// fence, then its status word), so every requester of a combined batch can watch ITS word and leave
+// as soon as its own page is there — a batch costs each caller its own page's decode, not the
+// slowest one's.  end waits for whatever is still pending, books the statistics and frees the lane;
+// it may run on another thread than begin.
+static const int32_t SMALL_PENDING = -1;
+
+extern "C" int cmb200_get_small_begin(cmb200_engine *e, size_t n, const cmb200_addr *addr, void *pages_out, cmb200_small_ticket *t) {
+	if (!t) return -1;
+	t->lane = -1; t->n = 0; t->status = nullptr;
 	if (n == 0) return 0;
+	if (n > cmb200_engine::GET_SMALL_MAX) { set_error_msg("cmb200_get_small_begin: more than 1024 requests"); return -1; }
 	if (!get_small_supports(e->bsize)) { set_error_msg("cmb200_get_small: page size not supported by the fused kernel"); return -2; }
-	std::shared_lock<std::shared_mutex> shared(e->get_rw);
-	// a free lane if there is one, else wait for the next in turn
+	e->get_gate.enter();
+	// a free lane if there is one, else wait for one
 	cmb200_engine::GetLane *ln = nullptr;
-	std::unique_lock<std::mutex> lk;
+	int li = -1;
 	const uint32_t first = e->lane_turn.fetch_add(1, std::memory_order_relaxed);
-	for (int k = 0; k < cmb200_engine::GET_LANES && !ln; k++) {
-		cmb200_engine::GetLane &c = e->lane[(first + k) % cmb200_engine::GET_LANES];
-		std::unique_lock<std::mutex> t(c.mu, std::try_to_lock);
-		if (t.owns_lock()) { ln = &c; lk = std::move(t); }
-	}
-	if (!ln) { ln = &e->lane[first % cmb200_engine::GET_LANES]; lk = std::unique_lock<std::mutex>(ln->mu); }
-	CMB_CHECK(cudaSetDevice(e->device));
-	static const int32_t PENDING = -1;
-	uint64_t rq = 0, ht = 0;
-	for (size_t at = 0; at < n; at += cmb200_engine::GET_SMALL_MAX) {
-		const uint32_t m = (uint32_t)((n - at < cmb200_engine::GET_SMALL_MAX) ? n - at : cmb200_engine::GET_SMALL_MAX);
-		// Requests and answers travel through page-locked host memory that the kernel reads and writes
-		// directly: no copy is queued before or after the launch, and the caller learns of the end by
-		// watching the status words flip (the kernel writes a page, fences, then its status), which costs
-		// a few microseconds where a stream synchronisation costs tens.
-		memcpy(ln->h_addr, addr + at, (size_t)m * 16);
-		volatile int32_t *hs = ln->h_status;
-		for (uint32_t i = 0; i < m; i++) hs[i] = PENDING;
-		GetJob job{};
-		job.table = e->table; job.arena = e->arena.base; job.arena_size = e->arena.size;
-		job.addr = (const unsigned long long *)ln->h_addr; job.valid = nullptr; job.n = m; job.nbytes = e->bsize;
-		job.out = (uint8_t *)pages_out + at * e->bsize;          // device memory or page-locked host memory (UVA)
-		job.status = ln->h_status;
-		for (int r = 0; r < GET_MAX_PEERS; r++) { job.peer[r] = e->peer_base[r]; job.peer_size[r] = e->peer_size[r]; }
-		job.scratch = e->d_scratch; job.region_entries = e->region_entries; job.pool_bits = e->d_pool_bits; job.pool_n = e->pool_n;
-		if (launch_get_small(job, ln->st)) return -1;
-		uint32_t done = 0;
-		for (uint64_t spins = 0; done < m;) {
-			if (hs[done] != PENDING) { done++; continue; }
-#if defined(__x86_64__)
-			__builtin_ia32_pause();
-#endif
-			if (++spins > 20000) {                                // ~1 ms of polling: a large batch, let the driver wait
-				CMB_CHECK(cudaStreamSynchronize(ln->st));
-				spins = 0;
-				if (hs[done] == PENDING) { set_error_msg("cmb200_get_small: kernel finished without an answer"); return -1; }
-			}
+	for (uint64_t spins = 0; !ln; spins++) {
+		for (int k = 0; k < cmb200_engine::GET_LANES && !ln; k++) {
+			const int c = (int)((first + k) % cmb200_engine::GET_LANES);
+			int idle = 0;
+			if (e->lane[c].busy.compare_exchange_strong(idle, 1, std::memory_order_acq_rel)) { ln = &e->lane[c]; li = c; }
 		}
-		__atomic_thread_fence(__ATOMIC_ACQUIRE);
-		memcpy(status_out + at, ln->h_status, (size_t)m * 4);
-		for (uint32_t i = 0; i < m; i++) {
-			if (status_out[at + i] != CMB200_INVALID) rq++;
-			if (status_out[at + i] == CMB200_HIT) ht++;
+		if (!ln) sched_yield();
+	}
+	if (cudaSetDevice(e->device) != cudaSuccess) { ln->busy.store(0, std::memory_order_release); e->get_gate.leave(); return -1; }
+	// Requests and answers travel through page-locked host memory that the kernel reads and writes
+	// directly: no copy is queued before or after the launch, and the end is seen by watching the
+	// status words flip, which costs a few microseconds where a stream synchronisation costs tens.
+	memcpy(ln->h_addr, addr, n * 16);
+	volatile int32_t *hs = ln->h_status;
+	for (size_t i = 0; i < n; i++) hs[i] = SMALL_PENDING;
+	GetJob job{};
+	job.table = e->table; job.arena = e->arena.base; job.arena_size = e->arena.size;
+	job.addr = (const unsigned long long *)ln->h_addr; job.valid = nullptr; job.n = (uint32_t)n; job.nbytes = e->bsize;
+	job.out = (uint8_t *)pages_out;                          // device memory or page-locked host memory (UVA)
+	job.status = ln->h_status;
+	for (int r = 0; r < GET_MAX_PEERS; r++) { job.peer[r] = e->peer_base[r]; job.peer_size[r] = e->peer_size[r]; }
+	job.scratch = e->d_scratch; job.region_entries = e->region_entries; job.pool_bits = e->d_pool_bits; job.pool_n = e->pool_n;
+	if (launch_get_small(job, ln->st)) { ln->busy.store(0, std::memory_order_release); e->get_gate.leave(); return -1; }
+	t->lane = li; t->n = (uint32_t)n; t->status = ln->h_status;
+	return 0;
+}
+
+extern "C" int cmb200_get_small_end(cmb200_engine *e, cmb200_small_ticket *t, int32_t *status_out) {
+	if (!t || t->lane < 0) return 0;
+	cmb200_engine::GetLane *ln = &e->lane[t->lane];
+	volatile int32_t *hs = ln->h_status;
+	int rc = 0;
+	uint32_t done = 0;
+	for (uint64_t spins = 0; done < t->n;) {
+		if (hs[done] != SMALL_PENDING) { done++; continue; }
+#if defined(__x86_64__)
+		__builtin_ia32_pause();
+#endif
+		if (++spins > 20000) {                                // ~1 ms of polling: a large batch, let the driver wait
+			if (cudaSetDevice(e->device) != cudaSuccess || cudaStreamSynchronize(ln->st) != cudaSuccess) {
+				cmb_set_error("cudaStreamSynchronize(small get)", cudaGetLastError(), __FILE__, __LINE__);
+				rc = -1; break;
+			}
+			spins = 0;
+			if (hs[done] == SMALL_PENDING) { set_error_msg("cmb200_get_small: kernel finished without an answer"); rc = -1; break; }
+		}
+	}
+	__atomic_thread_fence(__ATOMIC_ACQUIRE);
+	if (rc == 0) {
+		uint64_t rq = 0, ht = 0;
+		for (uint32_t i = 0; i < t->n; i++) {
+			const int32_t st = hs[i];
+			if (status_out) status_out[i] = st;
+			if (st != CMB200_INVALID) rq++;
+			if (st == CMB200_HIT) ht++;
 		}
 		e->small_get_launches++;
+		e->small_get_requests += rq; e->small_get_hits += ht;
 	}
-	e->small_get_requests += rq; e->small_get_hits += ht;
+	t->lane = -1;
+	ln->busy.store(0, std::memory_order_release);
+	e->get_gate.leave();
+	return rc;
+}
+
+extern "C" int cmb200_get_small(cmb200_engine *e, size_t n, const cmb200_addr *addr, void *pages_out, int32_t *status_out) {
+	for (size_t at = 0; at < n; at += cmb200_engine::GET_SMALL_MAX) {
+		const size_t m = n - at < cmb200_engine::GET_SMALL_MAX ? n - at : cmb200_engine::GET_SMALL_MAX;
+		cmb200_small_ticket t;
+		const int rc = cmb200_get_small_begin(e, m, addr + at, (uint8_t *)pages_out + at * e->bsize, &t);
+		if (rc) return rc;
+		if (cmb200_get_small_end(e, &t, status_out + at)) return -1;
+	}
 	return 0;
 }
 
 // ---- peers: the other ranks' arenas, mapped for NVLink reads -------------------------------------
 
 extern "C" int cmb200_close_peers(cmb200_engine *e) {
-	std::unique_lock<std::shared_mutex> g(e->get_rw);      // no small get in flight
+	cmb200_engine::GateClosed g(e->get_gate);             // no small get in flight
 	CMB_CHECK(cudaSetDevice(e->device));
 	for (int r = 0; r < GET_MAX_PEERS; r++) {
 		if (e->peer_base[r]) cudaIpcCloseMemHandle((void *)e->peer_base[r]);
@@ -782,7 +844,7 @@ extern "C" int cmb200_arena_ipc_handle(cmb200_engine *e, void *handle64, uint64_
 
 extern "C" int cmb200_open_peer(cmb200_engine *e, uint32_t rank, const void *handle64, uint64_t arena_bytes) {
 	if (rank >= GET_MAX_PEERS) { set_error_msg("cmb200_open_peer: rank out of range"); return -1; }
-	std::unique_lock<std::shared_mutex> g(e->get_rw);
+	cmb200_engine::GateClosed g(e->get_gate);
 	CMB_CHECK(cudaSetDevice(e->device));
 	cudaIpcMemHandle_t h;
 	memcpy(&h, handle64, 64);
@@ -1063,7 +1125,7 @@ extern "C" int cmb200_load(cmb200_engine *e, const char *path, uint64_t *records
 // to overflow although a good part of it is garbage (filemap_make_room, cmb200_compact).
 extern "C" int cmb200_compact(cmb200_engine *e, uint64_t *reclaimed_out) {
 	std::lock_guard<std::mutex> g(e->mu);
-	std::unique_lock<std::shared_mutex> gg(e->get_rw);  // records move: no small get may be reading the arena
+	cmb200_engine::GateClosed gg(e->get_gate);          // records move: no small get may be reading the arena
 	unsigned long long c[8];
 	if (read_counters(e, c)) return -1;
 	harvest_pending(e, true);

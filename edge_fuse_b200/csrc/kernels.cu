@@ -888,8 +888,16 @@ __device__ bool gs_sections_fit(const DecodeCta *dc, uint32_t clen, uint32_t n) 
 	return dc->ip1[prev] == clen && dc->op1[prev] == n;          // filemap.c:244-248: consumed == compressed_length
 }
 
+#ifdef CMB_GS_TRACE            /* diagnostic builds only: cycle stamps of the phases, printed by CTA 0 */
+#define GS_STAMP(k) do { if (tid == 0) stamp[k] = clock64(); } while (0)
+#else
+#define GS_STAMP(k) do { } while (0)
+#endif
 __global__ void __launch_bounds__(GS_THREADS, 1) k_get_small(GetJob job) {
 	extern __shared__ __align__(128) uint8_t smem[];
+#ifdef CMB_GS_TRACE
+	long long stamp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
 	GetShared *sh = reinterpret_cast<GetShared *>(smem);
 	DecodeCta *dc = reinterpret_cast<DecodeCta *>(smem + 128);
 	uint8_t *rec = smem + GS_CTRL;
@@ -901,6 +909,7 @@ __global__ void __launch_bounds__(GS_THREADS, 1) k_get_small(GetJob job) {
 	uint8_t *out = job.out + (size_t)i * job.nbytes;
 	const uint32_t s_bar = smem_addr(&sh->bar);
 	if (job.valid && !job.valid[i]) { if (tid == 0) job.status[i] = ST_INVALID; return; }
+	GS_STAMP(0);
 	if (tid == 0) {
 		sh->region = 0xffffffffu;
 		mbar_init(s_bar, 1u);
@@ -955,11 +964,11 @@ __global__ void __launch_bounds__(GS_THREADS, 1) k_get_small(GetJob job) {
 			// raw page (filemap.c:249-251); 8-byte granularity: rec + 24 is not 16-byte aligned
 			for (uint32_t k = tid; k < job.nbytes / 8u; k += GS_THREADS)
 				reinterpret_cast<unsigned long long *>(out)[k] = reinterpret_cast<const unsigned long long *>(rec + 24)[k];
-			__threadfence_system();
 			result = ST_HIT;
 			break;
 		}
 		// ---- LZ4 block -> page, both in shared memory (lz4_decode_cta.cuh) ----
+		GS_STAMP(1);
 		if (tid == 0) {
 			if (sh->region == 0xffffffffu) sh->region = gs_region_take(job);
 			gs_sections(job, sh, dc, clen, st == ST_HIT);
@@ -970,6 +979,7 @@ __global__ void __launch_bounds__(GS_THREADS, 1) k_get_small(GetJob job) {
 		const uint32_t stride = dc_stride(job.nbytes);
 		const uint32_t blk_s = smem_addr(rec + 24), page_s = smem_addr(page);
 		bool good = false;
+		GS_STAMP(2);
 		for (int pass = 0; pass < 2 && !good; pass++) {
 			const bool many = sh->sections > 1u;
 			if (dc->ip0[warp] != 0xffffffffu)
@@ -984,17 +994,30 @@ __global__ void __launch_bounds__(GS_THREADS, 1) k_get_small(GetJob job) {
 			__syncthreads();
 		}
 		if (!good) { result = ST_BAD_DECODE; break; }             // filemap.c:244-248
+		GS_STAMP(3);
+#ifndef CMB_DC_SKIP_LIT       /* diagnostic builds only: what a phase costs */
 		dc_literals(dc, desc, stride, blk_s, page_s, rec + 24, page, warp, lane);
+#endif
 		__syncthreads();
+		GS_STAMP(4);
+#ifndef CMB_DC_SKIP_MATCH
 		if (warp == 0) dc_matches(dc, desc, stride, page_s, lane);
+#endif
 		__syncthreads();
+		GS_STAMP(5);
 		for (uint32_t k = tid; k < job.nbytes / 16u; k += GS_THREADS)
 			reinterpret_cast<uint4 *>(out)[k] = reinterpret_cast<const uint4 *>(page)[k];
-		__threadfence_system();                           // `out` may be host memory that is read as soon as the status flips
+		GS_STAMP(6);
 		result = ST_HIT;
 		break;
 	}
+#ifdef CMB_GS_TRACE
+	if (tid == 0 && blockIdx.x == 0 && stamp[6])
+		printf("gs_trace clen %u sections %u: stage %lld sections %lld parse %lld literals %lld matches %lld out %lld (cycles)\n", sh->clen, sh->sections,
+		    stamp[1] - stamp[0], stamp[2] - stamp[1], stamp[3] - stamp[2], stamp[4] - stamp[3], stamp[5] - stamp[4], stamp[6] - stamp[5]);
+#endif
 	// status may live in page-locked host memory that the caller polls: the page first, then the status
+	// (every thread's stores happen before the barrier, thread 0's system-wide fence after it is cumulative)
 	__syncthreads();
 	if (tid == 0) {
 		if (sh->region != 0xffffffffu) gs_region_give(job, sh->region);

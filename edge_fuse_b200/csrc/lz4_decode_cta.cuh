@@ -36,7 +36,7 @@ namespace cmb {
 constexpr uint32_t DC_CHAINS = 16;                 // parse sections = warps of the CTA
 constexpr uint32_t DC_THREADS = DC_CHAINS * 32;
 constexpr uint32_t DC_LANE_LIT = 64;               // literal runs up to this are copied by one lane
-constexpr uint32_t DC_LANE_MATCH = 32;             // matches up to this are copied by one lane
+constexpr uint32_t DC_LANE_MATCH = 16;             // matches up to this are copied by one lane
 
 struct DecodeCta {                                 // shared memory
 	uint32_t ip0[DC_CHAINS], op0[DC_CHAINS];   // section start: block offset of its first token, output position; ip0 = ~0: empty
@@ -52,6 +52,8 @@ __host__ __device__ inline uint32_t dc_stride(uint32_t n) { return n / DC_CHAINS
 __host__ __device__ inline uint32_t dc_region(uint32_t n) { return DC_CHAINS * dc_stride(n); }   // entries of 16 bytes
 
 __device__ __forceinline__ uint32_t dcs_ld8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t dcs_ld32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void dcs_st32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v)); }
 __device__ __forceinline__ void dcs_st8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v)); }
 
 // LZ4 255-run length extension at shared address blk + ip; cap = block length
@@ -81,6 +83,7 @@ __device__ void dc_parse_chain(DecodeCta *dc, uint32_t c, uint32_t blk, uint32_t
 	uint32_t ip = dc->ip0[c], op = dc->op0[c];
 	const uint32_t op_end = dc->op_end[c];
 	uint32_t cnt = 0;
+	uint4 *dnext = desc;
 	int32_t err = 0;
 	if (ip >= cap) err = -1;
 	uint32_t tok = err ? 0u : dcs_ld8(blk + ip), b0 = err ? 0u : dcs_ld8(blk + ip + 1u);
@@ -93,18 +96,25 @@ __device__ void dc_parse_chain(DecodeCta *dc, uint32_t c, uint32_t blk, uint32_t
 			const uint32_t flen = l4 + (lx ? b0 : 0u);
 			const uint32_t fsrc = ip + 1u + lx;
 			const uint32_t ip2 = fsrc + flen, op2 = op + flen;
-			const uint32_t a = blk + ip2;
-			const uint32_t o0 = dcs_ld8(a), o1 = dcs_ld8(a + 1u), m0 = dcs_ld8(a + 2u);
+			// offset (2 bytes), match-length byte, and the next token with its follower are the five bytes
+			// at ip2 (the token follows the offset directly when there is no match-length byte): two
+			// aligned words cover them, so everything the next iteration needs arrives in ONE round trip
+			const uint32_t a = blk + ip2, s8 = (a & 3u) * 8u;
+			const uint32_t lo = dcs_ld32(a & ~3u), hi = dcs_ld32((a & ~3u) + 4u);
+			const uint32_t w = __funnelshift_r(lo, hi, s8);          // bytes ip2 .. ip2 + 3
+			const uint32_t b4 = (hi >> s8) & 0xffu;                 // byte ip2 + 4
+			const uint32_t m0 = (w >> 16) & 0xffu, b3 = w >> 24;
 			const uint32_t nip = ip2 + 2u + mx;
-			const uint32_t t1 = dcs_ld8(blk + nip), t2 = dcs_ld8(blk + nip + 1u);
-			const uint32_t off = o0 | (o1 << 8);
+			const uint32_t t1 = mx ? b3 : m0, t2 = mx ? b4 : b3;
+			const uint32_t off = w & 0xffffu;
 			const uint32_t fm = m4 + (mx ? m0 : 0u);
 			const uint32_t op3 = op2 + fm + 4u;
 			// nip <= cap covers ip + 2 < cap; op3 + 5 <= n covers "not the last literals" (op2 + 8 <= n);
 			// flen / fm == 270 <=> an extension byte of 255; off - 1 >= op2 <=> off == 0 or off > op2
 			const bool rare = nip > cap || flen == 270u || fm == 270u || off - 1u >= op2 || op3 + 5u > n || cnt >= max_desc;
 			if (!rare) {
-				if (lane == 0) desc[cnt] = make_uint4(fsrc, op, flen, off | (fm << 16));
+				if (lane == 0) *dnext = make_uint4(fsrc, op, flen, off | (fm << 16));
+				dnext++;
 				cnt++;
 				ip = nip; op = op3; tok = t1; b0 = t2;
 				continue;
@@ -142,7 +152,8 @@ __device__ void dc_parse_chain(DecodeCta *dc, uint32_t c, uint32_t blk, uint32_t
 		} else {
 			mlen = 0;
 		}
-		if (lane == 0) desc[cnt] = make_uint4(lit_src, out_pos, len, off | (mlen << 16));
+		if (lane == 0) *dnext = make_uint4(lit_src, out_pos, len, off | (mlen << 16));
+		dnext++;
 		cnt++;
 		if (last) break;                                     // op == n, ip == bytes consumed (lz4.c:1339)
 	}
@@ -189,24 +200,69 @@ __device__ void dc_literals(const DecodeCta *dc, const uint4 *desc, uint32_t str
 	}
 }
 
+__device__ __forceinline__ uint4 dcs_ld128(uint32_t a) {
+	uint4 v;
+	asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+	return v;
+}
+__device__ __forceinline__ void dcs_st128(uint32_t a, uint4 v) {
+	asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
+}
+
+// Bytes [k0, k1) of a match that repeats the `off` bytes before it (off < 32): byte k = from[k mod off].
+// Lanes only read bytes that were complete before the sequence began.
+__device__ __forceinline__ void dc_periodic_bytes(uint32_t to, uint32_t from, uint32_t off, uint32_t k0, uint32_t k1, int lane) {
+	uint32_t r = (k0 + (uint32_t)lane) % off;
+	const uint32_t step = 32u % off;
+	for (uint32_t k = k0 + lane; k < k1; k += 32u) {
+		dcs_st8(to + k, dcs_ld8(from + r));
+		r += step;
+		if (r >= off) r -= off;
+	}
+}
+
 // A match longer than a lane should copy: all 32 lanes.  to / from = shared addresses.
 __device__ __forceinline__ void dc_match_wide(uint32_t to, uint32_t from, uint32_t off, uint32_t len, int lane) {
-	if (off >= 32u) {
+	if (off >= 136u && len >= 64u) {
+		// 128 bytes per step: a 4-byte word per lane, destination aligned (up to 3 bytes go first), source
+		// word put together from the two aligned words around it; a step reads at most 132 bytes from its
+		// source position, all of them below what the step writes
+		const uint32_t head = (4u - (to & 3u)) & 3u;
+		if ((uint32_t)lane < head) dcs_st8(to + lane, dcs_ld8(from + lane));
+		uint32_t k = head;
+		for (; k + 128u <= len; k += 128u) {
+			const uint32_t a = from + k + 4u * lane, s8 = (a & 3u) * 8u;
+			const uint32_t lo = dcs_ld32(a & ~3u), hi = dcs_ld32((a & ~3u) + 4u);
+			dcs_st32(to + k + 4u * lane, __funnelshift_r(lo, hi, s8));
+			__syncwarp();
+		}
+		for (; k < len; k += 32u) {
+			if (k + lane < len) dcs_st8(to + k + lane, dcs_ld8(from + k + lane));
+			__syncwarp();
+		}
+	} else if (off >= 32u) {
 		// a step of 32 bytes only reads bytes that earlier steps (or earlier sequences) wrote
 		for (uint32_t k0 = 0; k0 < len; k0 += 32u) {
 			if (k0 + lane < len) dcs_st8(to + k0 + lane, dcs_ld8(from + k0 + lane));
 			__syncwarp();
 		}
+	} else if (len < 4096u) {
+		dc_periodic_bytes(to, from, off, 0u, len, lane);
 	} else {
-		// periodic extension of the `off` bytes before the match: lanes only read bytes that were
-		// complete before this sequence began; k mod off is carried along (k grows by 32)
-		uint32_t r = (uint32_t)lane % off;
-		const uint32_t step = 32u % off;
-		for (uint32_t k = lane; k < len; k += 32u) {
-			dcs_st8(to + k, dcs_ld8(from + r));
-			r += step;
-			if (r >= off) r -= off;
+		// A long run of a short pattern (a zero page is ONE such match): the first `head + period` bytes
+		// byte by byte, where period = a multiple of both off and 16 that is >= 512 and head aligns the
+		// rest to 16 bytes; from there every 16-byte word equals the one `period` bytes before it, and a
+		// step of 32 lanes x 16 bytes only reads what earlier steps wrote.
+		const uint32_t period = 16u * off * ((512u + 16u * off - 1u) / (16u * off));
+		const uint32_t first = ((16u - (to & 15u)) & 15u) + period;
+		dc_periodic_bytes(to, from, off, 0u, first, lane);
+		__syncwarp();
+		uint32_t k = first;
+		for (; k + 512u <= len; k += 512u) {
+			dcs_st128(to + k + 16u * lane, dcs_ld128(to + k + 16u * lane - period));
+			__syncwarp();
 		}
+		dc_periodic_bytes(to, from, off, k, len, lane);
 	}
 	__syncwarp();
 }
@@ -239,10 +295,12 @@ __device__ void dc_matches(const DecodeCta *dc, const uint4 *desc, uint32_t stri
 			// the last earlier match that my source touches (every one I depend on is at or below it)
 			const int dep = (cand >= 0 && ti + li > from) ? cand : -1;
 			const bool wide = len > DC_LANE_MATCH;
+			const uint32_t wides = __ballot_sync(CMB_FULL, wide);
 			uint32_t pending = __ballot_sync(CMB_FULL, valid);
+			const uint32_t src = out + from, dst = out + to;
 			while (pending) {
 				const int first = __ffs(pending) - 1;
-				if (__shfl_sync(CMB_FULL, (int)wide, first)) {
+				if ((wides >> first) & 1u) {
 					dc_match_wide(out + __shfl_sync(CMB_FULL, to, first), out + __shfl_sync(CMB_FULL, from, first),
 					    __shfl_sync(CMB_FULL, off, first), __shfl_sync(CMB_FULL, len, first), lane);
 					pending &= ~(1u << first);
@@ -252,10 +310,24 @@ __device__ void dc_matches(const DecodeCta *dc, const uint4 *desc, uint32_t stri
 				const uint32_t runs = __ballot_sync(CMB_FULL, run);
 				const uint32_t mine = run ? len : 0u;
 				const uint32_t most = __reduce_max_sync(CMB_FULL, mine);
-				const uint32_t src = out + from, dst = out + to;
-				// byte by byte in order: a match that overlaps itself reads what it has just written
-				for (uint32_t k = 0; k < most; k++)
-					if (k < mine) dcs_st8(dst + k, dcs_ld8(src + k));
+				// Byte k of a match is byte k mod off of the `off` bytes before it (a match that overlaps
+				// itself repeats them), all of which exist before the match starts: four loads, then four
+				// stores, no load waits for a store of its own match.
+				uint32_t r = 0;
+				for (uint32_t k = 0; k < most; k += 4u) {
+					const uint32_t r0 = r, r1 = r0 + 1u == off ? 0u : r0 + 1u, r2 = r1 + 1u == off ? 0u : r1 + 1u,
+					    r3 = r2 + 1u == off ? 0u : r2 + 1u;
+					r = r3 + 1u == off ? 0u : r3 + 1u;
+					uint32_t v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+					if (k < mine) v0 = dcs_ld8(src + r0);
+					if (k + 1u < mine) v1 = dcs_ld8(src + r1);
+					if (k + 2u < mine) v2 = dcs_ld8(src + r2);
+					if (k + 3u < mine) v3 = dcs_ld8(src + r3);
+					if (k < mine) dcs_st8(dst + k, v0);
+					if (k + 1u < mine) dcs_st8(dst + k + 1u, v1);
+					if (k + 2u < mine) dcs_st8(dst + k + 2u, v2);
+					if (k + 3u < mine) dcs_st8(dst + k + 3u, v3);
+				}
 				__syncwarp();
 				pending &= ~runs;
 			}

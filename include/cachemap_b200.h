@@ -192,6 +192,23 @@ int cmb200_close_peers(cmb200_engine *e);
  * cmb200_get_batch.  status_out as cmb200_get_batch. */
 int cmb200_get_small(cmb200_engine *e, size_t n, const cmb200_addr *addr, void *pages_out, int32_t *status_out);
 
+/* The same get in two halves, for callers that combine the requests of several threads into one
+ * launch (the drop-in's combining queue, cachemap_api.c): begin (n <= 1024) launches and returns;
+ * ticket.status[i] — page-locked host memory the kernel writes — holds CMB200_SMALL_PENDING until
+ * request i is answered, and page i is complete in pages_out once its status is (read the status
+ * with acquire semantics), so every requester can leave when ITS page is there instead of when
+ * the slowest page of the batch is.  end waits for the rest, copies the statuses (status_out may
+ * be NULL), books the statistics and releases the ticket's engine lane; it may be called from
+ * another thread than begin, exactly once per successful begin. */
+#define CMB200_SMALL_PENDING (-1)
+typedef struct cmb200_small_ticket {
+	int lane;                        /* engine lane the launch runs on, -1 = nothing in flight */
+	uint32_t n;
+	const volatile int32_t *status;
+} cmb200_small_ticket;
+int cmb200_get_small_begin(cmb200_engine *e, size_t n, const cmb200_addr *addr, void *pages_out, cmb200_small_ticket *ticket);
+int cmb200_get_small_end(cmb200_engine *e, cmb200_small_ticket *ticket, int32_t *status_out);
+
 /* Lookup only: status_out[i] in CMB200_{MISS,HIT,BAD_ENTRY,REMOTE}; owner_out[i] = owning rank for
  * CMB200_REMOTE. */
 int cmb200_locate_batch(cmb200_engine *e, size_t n, const cmb200_addr *addr, int32_t *status_out,

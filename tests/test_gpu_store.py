@@ -1010,3 +1010,122 @@ def test_compaction_rebuilds_a_table_full_of_tombstones(E, gpu):
     out, st = eng.get(u, l)
     assert (st == E.HIT).all() and (out == pages[200:400]).all() and eng.stats()["entries"] == 500
     eng.close()
+
+
+@pytest.mark.gpu
+def test_small_get_walks_records_with_and_without_checkpoints(E, gpu, oracle, tmp_path, monkeypatch):
+    """k_get_small parses a record in 16 sections when the encoder left checkpoints for it and with
+    one warp otherwise (engine without the side table, records loaded from a snapshot, records moved
+    by a compaction): the pages must be the same bytes either way, for every content class and for
+    ragged compressibility (checkpoint sections that are empty, a page that is ONE sequence)."""
+    bs = 65536
+    kinds = "RTZMPAX"
+    n = 84
+    pages = np.stack([datagen.make_page(kinds[i % len(kinds)], bs, 900 + i) for i in range(n)])
+    pages[3, :] = 0                                            # one match over the whole page
+    pages[4, :40000] = 7                                       # long run, then noise
+    u = np.full(n, 77, dtype=np.uint64)
+    l = np.arange(n, dtype=np.uint64)
+
+    eng = E.Engine(pshift=16, accel=12, capacity=4096, arena_bytes=64 << 20, max_batch=64)
+    eng.put(u, l, pages)
+    out, st = eng.get_small(u, l)
+    assert (st == E.HIT).all() and (out == pages).all()
+    # stored blocks are the reference's bytes, so the oracle decodes them to the same pages
+    snap = str(tmp_path / "ck.snap")
+    eng.save(snap)
+    # compaction moves the records: their checkpoints no longer name them (one-warp walk), same pages
+    eng.unset(u[:10], l[:10])
+    eng.compact()
+    out, st = eng.get_small(u, l)
+    assert (st[:10] == E.MISS).all() and (st[10:] == E.HIT).all() and (out[10:] == pages[10:]).all()
+    # rewriting a key renews its checkpoints
+    eng.put(u[10:20], l[10:20], pages[30:40])
+    out, st = eng.get_small(u[10:20], l[10:20])
+    assert (st == E.HIT).all() and (out == pages[30:40]).all()
+    eng.close()
+
+    # records that arrive from a snapshot have no checkpoints
+    eng = E.Engine(pshift=16, accel=12, capacity=4096, arena_bytes=64 << 20, max_batch=64)
+    eng.load(snap)
+    out, st = eng.get_small(u, l)
+    assert (st == E.HIT).all() and (out == pages).all()
+    eng.close()
+
+    # an engine without the side table
+    monkeypatch.setenv("CMB200_CKPT", "0")
+    eng = E.Engine(pshift=16, accel=12, capacity=4096, arena_bytes=64 << 20, max_batch=64)
+    eng.put(u, l, pages)
+    out, st = eng.get_small(u, l)
+    assert (st == E.HIT).all() and (out == pages).all()
+    eng.close()
+
+
+@pytest.mark.gpu
+def test_small_get_in_two_halves(E, gpu):
+    """cmb200_get_small_begin / _end: the statuses appear one by one in the ticket's page-locked
+    words (PENDING until then), a page is complete once its status is, and end may run on another
+    thread than begin."""
+    import ctypes as C
+    import threading
+    bs = 65536
+    kinds = "RTZM"
+    n = 24
+    pages = np.stack([datagen.make_page(kinds[i % 4], bs, 40 + i) for i in range(n)])
+    eng = E.Engine(pshift=16, accel=12, capacity=4096, arena_bytes=64 << 20, max_batch=64)
+    u = np.full(n, 5, dtype=np.uint64)
+    l = np.arange(n, dtype=np.uint64)
+    eng.put(u, l, pages)
+    L = E.lib()
+
+    class Ticket(C.Structure):
+        _fields_ = [("lane", C.c_int), ("n", C.c_uint32), ("status", C.POINTER(C.c_int32))]
+
+    addr = np.stack([np.append(u, 6), np.append(l, 0)], axis=1).astype(np.uint64).copy()   # last one misses
+    m = n + 1
+    buf = L.cmb200_host_alloc(m * bs)
+    for rounds in range(3):
+        t = Ticket()
+        assert L.cmb200_get_small_begin(eng.h, m, addr.ctypes.data, buf, C.byref(t)) == 0
+        assert t.lane >= 0 and t.n == m
+        got = np.zeros(m, dtype=bool)
+        arr = np.ctypeslib.as_array((C.c_uint8 * (m * bs)).from_address(buf)).reshape(m, bs)
+        while not got.all():
+            for i in range(m):
+                if not got[i] and t.status[i] != -1:
+                    # the page is there as soon as its status is
+                    if i < n:
+                        assert t.status[i] == E.HIT and (arr[i] == pages[i]).all()
+                    else:
+                        assert t.status[i] == E.MISS
+                    got[i] = True
+        st = np.zeros(m, dtype=np.int32)
+        rc = []
+        th = threading.Thread(target=lambda: rc.append(L.cmb200_get_small_end(eng.h, C.byref(t), st.ctypes.data)))
+        th.start()
+        th.join()
+        assert rc == [0] and t.lane == -1
+        assert (st[:n] == E.HIT).all() and st[n] == E.MISS
+    # more launches in flight than the engine has lanes: begin waits for a lane, nothing is lost
+    tickets = []
+    bufs = []
+
+    def one(i):
+        b = L.cmb200_host_alloc(bs)
+        t = Ticket()
+        a = addr[i:i + 1].copy()
+        assert L.cmb200_get_small_begin(eng.h, 1, a.ctypes.data, b, C.byref(t)) == 0
+        s1 = np.zeros(1, dtype=np.int32)
+        assert L.cmb200_get_small_end(eng.h, C.byref(t), s1.ctypes.data) == 0
+        page = np.ctypeslib.as_array((C.c_uint8 * bs).from_address(b)).copy()
+        L.cmb200_host_free(b)
+        tickets.append((i, int(s1[0]), page))
+
+    ths = [threading.Thread(target=one, args=(i % n,)) for i in range(96)]
+    [x.start() for x in ths]
+    [x.join() for x in ths]
+    assert len(tickets) == 96
+    for i, s1, page in tickets:
+        assert s1 == E.HIT and (page == pages[i]).all()
+    L.cmb200_host_free(buf)
+    eng.close()

@@ -66,9 +66,14 @@ def main():
             cm = L.cachemap_create(d.encode(), 1 << 16, 12, 16)
             L.cachemap_put(cm, 1 << 40, 1, 0, pages[0].ctypes.data)      # engine start outside the clock
             put = run(L, cm, pages, threads, a.per_thread, False)
+            st0 = E.engine_stats(L.cachemap_engine(cm)) if hasattr(E, "engine_stats") else None
             get = run(L, cm, pages, threads, a.per_thread, True)
+            st1 = E.engine_stats(L.cachemap_engine(cm)) if hasattr(E, "engine_stats") else None
             L.cachemap_free(cm)
         out[f"ours_T{threads}"] = {"put_gibs": put[0], "put_kops": put[1] / 1e3, "get_gibs": get[0], "get_kops": get[1] / 1e3}
+        if st0 and st1:    # gets that reached the GPU and the launches that carried them
+            out[f"ours_T{threads}"]["gpu_gets"] = st1["get_requests"] - st0["get_requests"]
+            out[f"ours_T{threads}"]["get_launches"] = st1["kernel_launches"] - st0["kernel_launches"]
         print(threads, out[f"ours_T{threads}"], flush=True)
     from oracle import ef_oracle as O
     R = O.ref()

@@ -6,7 +6,7 @@ n = 64
 eng = E.Engine(pshift=16, accel=12, capacity=1 << 14, arena_bytes=1 << 30, max_batch=1024)
 hp = E.lib().cmb200_host_alloc(n * 65536)
 row = {}
-for k, cls in ((1, "T"), (3, "M")):
+for k, cls in [(k, c) for k, c in enumerate("RTZM") if c in os.environ.get("CLASSES", "TM")]:
     allc = np.arange(16 * n, dtype=np.uint64)
     cids = allc[((allc + (allc >> np.uint64(3))) & np.uint64(3)) == k][:n]
     pages = np.stack([E.gen_chunk_host(42, int(c), 65536) for c in cids])
