@@ -12,7 +12,6 @@
 #include "fingerprint.cuh"
 #include "lz4_encode.cuh"
 #include "lz4_encode_ring.cuh"
-#include "lz4_encode_groups.cuh"
 #include <type_traits>
 #include "lz4_decode.cuh"
 #include "lz4_decode_cta.cuh"
@@ -345,9 +344,8 @@ __device__ uint32_t commit_direct(const EncodeJob &job, uint32_t i, uint32_t idx
 	return need;
 }
 
-// ENC 0: lean loop, page read through the L1.  ENC 1: lean loop, parse frontier staged in a per-warp
-// shared-memory ring by TMA (lz4_encode_ring.cuh); shared memory = tables | rings | mbarriers.
-// ENC 2: the round-1 loop (lz4_encode.cuh), kept for comparison.
+// ENC 0: page read through the L1.  ENC 1: parse frontier staged in a per-warp shared-memory ring
+// by TMA (lz4_encode_ring.cuh); shared memory = tables | rings | mbarriers.
 // FPNA: the fingerprint's streaming loads do not allocate in the L1.
 // Launch bounds = the real launch shapes (2 CTAs x 7 warps, or 1 CTA x 13 warps with the ring), so
 // that the register allocator may use what the SM has (146 / 157 registers per thread) instead of
@@ -416,12 +414,10 @@ __global__ void __launch_bounds__(ENC == 1 ? ENC_RING_WARPS * 32 : ENC_PLAIN_WAR
 		}
 		uint32_t clen, ck = 0xffffffffu;
 		if (job.fps) {                  // fingerprint along the parse frontier: the page is read once
-			if (ENC == 2) clen = lz4_encode_warp<WIDE, true, FPNA>(src, job.nbytes, dst, job.accel, wsm, lane, fp_hi, fp_lo);
-			else clen = lz4_encode_lean<WIDE, true, FPNA, ENC == 1>(src, job.nbytes, dst, job.accel, wsm, ring, lane, fp_hi, fp_lo, ck);
+			clen = lz4_encode_lean<WIDE, true, FPNA, ENC == 1>(src, job.nbytes, dst, job.accel, wsm, ring, lane, fp_hi, fp_lo, ck);
 			if (lane == 0) { job.fps[2 * (size_t)i] = fp_hi; job.fps[2 * (size_t)i + 1] = fp_lo; }
 		} else {
-			if (ENC == 2) clen = lz4_encode_warp<WIDE, false, false>(src, job.nbytes, dst, job.accel, wsm, lane, fp_hi, fp_lo);
-			else clen = lz4_encode_lean<WIDE, false, false, ENC == 1>(src, job.nbytes, dst, job.accel, wsm, ring, lane, fp_hi, fp_lo, ck);
+			clen = lz4_encode_lean<WIDE, false, false, ENC == 1>(src, job.nbytes, dst, job.accel, wsm, ring, lane, fp_hi, fp_lo, ck);
 		}
 		if (lane == 0) job.lens[i] = (int32_t)clen;
 		if (store) {
@@ -429,199 +425,16 @@ __global__ void __launch_bounds__(ENC == 1 ? ENC_RING_WARPS * 32 : ENC_PLAIN_WAR
 			if (in_arena) {
 				const uint32_t used = commit_direct(job, i, idx, base, clen, fp_hi, fp_lo, lane);
 				if (lane == 0) seg_cur += used;
-				if (ENC != 2) ckpt_store(job, idx, base, clen, ck, lane);
+				ckpt_store(job, idx, base, clen, ck, lane);
 			} else {
 				const unsigned long long at = commit_record(job, i, idx, dst, clen, (int32_t)clen, false, fp_hi, fp_lo, lane);
-				if (ENC != 2 && at != ~0ull) ckpt_store(job, idx, at, clen, ck, lane);
+				if (at != ~0ull) ckpt_store(job, idx, at, clen, ck, lane);
 			}
 		}
 	}
 	if (direct && lane == 0) { job.arena.seg[2 * gw] = seg_cur; job.arena.seg[2 * gw + 1] = seg_end; }
 }
 
-// ------------------------------------------------------------------------------------------
-// group-per-chunk encoder (see lz4_encode_groups.cuh): 8 lanes per chunk, tables in global memory
-// ------------------------------------------------------------------------------------------
-
-// filemap record {data_prefix, payload} into the arena + slot publish, by one 8-lane group
-// (same protocol as commit_record).
-__device__ void grp_commit_record(const GroupCtx &g, const EncodeJob &job, uint32_t i, uint32_t idx,
-    const uint8_t *payload, uint32_t plen, int32_t clen, bool payload_ro) {
-	Slot &s = job.table.slots[idx];
-	const uint32_t need = (24u + plen + 15u) & ~15u;
-	unsigned long long off = 0;
-	int ok = 1;
-	if (g.gl == 0) {
-		off = atomicAdd(job.arena.head, (unsigned long long)need);
-		if (off + need > job.arena.size) {
-			atomicAdd(job.arena.dropped, 1ull);      // no rollback, slot untouched: see commit_record
-			ok = 0;
-		}
-	}
-	ok = grp_shfl(g, ok, 0);
-	if (!ok) { if (g.gl == 0 && job.rec_out) job.rec_out[i] = ~0ull; return; }
-	off = grp_shfl(g, off, 0);
-	uint8_t *rec = job.arena.base + off;
-	const unsigned long long au = job.addr[2 * i], al = job.addr[2 * i + 1];
-	if (g.gl < 6) {
-		const uint32_t w = g.gl == 0 ? (uint32_t)au : g.gl == 1 ? (uint32_t)(au >> 32) : g.gl == 2 ? (uint32_t)al
-		    : g.gl == 3 ? (uint32_t)(al >> 32) : g.gl == 4 ? (uint32_t)clen : 0u;
-		reinterpret_cast<uint32_t *>(rec)[g.gl] = w;
-	}
-	if (payload_ro) grp_copy<true>(g, rec + 24, payload, plen);
-	else grp_copy<false>(g, rec + 24, payload, plen);
-	__threadfence();
-	__syncwarp(g.gmask);
-	if (g.gl == 0)
-		slot_publish(job, s, i, idx, off, need, (uint32_t)clen, au, al, job.fps ? job.fps[2 * (size_t)i] : 0ull,
-		    job.fps ? job.fps[2 * (size_t)i + 1] : 0ull);
-}
-
-template <bool WIDE>
-__global__ void __launch_bounds__(128, 6) k_encode_groups(EncodeJob job) {
-	typedef typename std::conditional<WIDE, uint32_t, uint16_t>::type slot_t;
-	const int lane = threadIdx.x & 31;
-	GroupCtx g;
-	g.gbase = lane & 24; g.gl = lane & 7; g.gmask = 0xffu << g.gbase;
-	const uint32_t ggroup = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
-	slot_t *const tab = reinterpret_cast<slot_t *>(job.gtab + (size_t)ggroup * LZ4_TABLE_BYTES);
-	const uint32_t n = job.nbytes, accel = job.accel;
-	const uint32_t lim4 = (n + 3u) & ~3u;
-	const uint32_t mflimit = n >= LZ4_MIN_INPUT ? n - LZ4_MATCH_FIND_MARGIN : 0u;
-	const uint32_t mlimit = n >= LZ4_MIN_INPUT ? n - LZ4_TAIL_LITERALS : 0u;
-	const bool store = job.slot_idx != nullptr;
-	uint32_t state = GS_NEW, idx = 0, sidx = 0, anchor = 0, op = 0, shift = 0, g0 = 0;
-	const uint8_t *src = job.pages;
-	uint8_t *dst = job.stage;
-
-	for (;;) {
-		if (__ballot_sync(CMB_FULL, state != GS_OUT) == 0u) break;
-		if (state == GS_NEW) {
-			uint32_t i = 0;
-			if (g.gl == 0) i = atomicAdd(job.work, 1u);
-			i = grp_shfl(g, i, 0);
-			if (i >= job.n) {
-				state = GS_OUT;
-			} else {
-				idx = i;
-				bool live = true;
-				if (store) {
-					sidx = job.slot_idx[i];
-					live = sidx != 0xffffffffu && job.table.slots[sidx].seq == job.seq0 + job.seq_stride * i;
-				}
-				src = job.pages + (size_t)i * job.page_stride;
-				dst = job.stage + (size_t)(store ? ggroup : i) * job.stage_stride;
-				if (!live) {
-					if (g.gl == 0) job.lens[i] = -1;
-				} else if (accel == 0) {       // raw page, compressed_length 0 (filemap.c:129-133)
-					if (g.gl == 0) job.lens[i] = 0;
-					if (store) grp_commit_record(g, job, i, sidx, src, n, 0, true);
-				} else {
-					uint4 *t4 = reinterpret_cast<uint4 *>(tab);              // lz4.c:739
-#pragma unroll 4
-					for (uint32_t j = g.gl; j < LZ4_TABLE_BYTES / 16; j += LZ4_G) t4[j] = make_uint4(0, 0, 0, 0);
-					__syncwarp(g.gmask);
-					anchor = 0; op = 0; shift = 0; g0 = 0;
-					state = n >= LZ4_MIN_INPUT ? GS_RUN : GS_TAIL;
-				}
-			}
-		} else if (state == GS_RUN) {
-			// ---- one batch of 8 table operations in program order ----
-			const uint32_t p0 = anchor + 1;
-			const uint32_t gs = g0 + (uint32_t)g.gl;
-			const bool special = gs < shift;                       // refill end-2 (gs 0), re-test end (gs 1)
-			const uint32_t k = gs - shift;
-			uint32_t pos = special ? anchor - 2u + 2u * gs : p0 + lz4_probe_off(k, accel);
-			const bool en = special || p0 + lz4_probe_off(k + 1, accel) <= mflimit;
-			pos = en ? pos : 0u;
-			const Lz4Around ai = lz4_around(src, pos);
-			const uint32_t h = WIDE ? lz4_hash5((uint64_t)ai.at | ((uint64_t)ai.next << 32)) : lz4_hash4(ai.at);
-			uint32_t cand = en ? (uint32_t)tab[h] : 0u;
-			const uint32_t peers = (__match_any_sync(g.gmask, en ? h : 0x10000u + (uint32_t)g.gl) >> g.gbase) & 0xffu;
-			const uint32_t lower = peers & ((1u << g.gl) - 1u);
-			const uint32_t prev_pos = grp_shfl(g, pos, lower ? 31 - __clz(lower) : g.gl);
-			if (lower) cand = prev_pos;                            // what the serial loop had stored by then
-			const Lz4Around ac = lz4_around(src, cand);
-			const bool hit = en && !(special && gs == 0u) && cand + LZ4_FAR >= pos && ac.at == ai.at;
-			const uint32_t hits = grp_ballot(g, hit);
-			const uint32_t enmask = grp_ballot(g, en);
-			uint32_t nf, nb;
-			{
-				const uint32_t xf = ai.next ^ ac.next;
-				nf = xf ? (uint32_t)(__ffs(xf) - 1) >> 3 : 4u;
-				nf = min(nf, mlimit - min(pos + LZ4_MIN_MATCH, mlimit));
-				const uint32_t xb = ai.before ^ ac.before;
-				nb = xb ? (uint32_t)__clz(xb) >> 3 : 4u;
-				nb = min(nb, min(pos - min(anchor, pos), cand));
-				if (special) nb = 0;
-			}
-			const int w = hits ? __ffs(hits) - 1 : LZ4_G - 1;
-			const uint32_t commit = hits ? (0xffu >> (LZ4_G - 1 - w)) : enmask;
-			if ((commit >> g.gl) & 1u) {
-				const uint32_t pc = peers & commit;
-				if (31 - __clz(pc) == g.gl) tab[h] = (slot_t)pos;      // last writer per slot wins
-			}
-			__syncwarp(g.gmask);
-			if (hits) {
-				const uint32_t ip = grp_shfl(g, pos, w), match = grp_shfl(g, cand, w);
-				uint32_t fwd = grp_shfl(g, nf, w), back = grp_shfl(g, nb, w);
-				if (fwd == 4u) fwd = 4u + grp_count(g, src, ip + 8u, match + 8u, mlimit, lim4);
-				if (back == 4u && ip >= anchor + 5u && match >= 5u) back = 4u + grp_catchup(g, src, ip - 4u, match - 4u, anchor);
-				const uint32_t off = ip - match, mc = back + fwd, lit = ip - back - anchor;
-				const uint32_t end = ip + LZ4_MIN_MATCH + fwd;
-				// ---- emit (lz4.c:625-683) ----
-				if (lit <= 32u && mc < 15u + 255u) {
-					uint8_t *o = dst + op;
-					const uint32_t hl = 1u + (lit >= 15u), mext = mc >= 15u, tail = hl + lit;
-					const uint32_t lw = lane_word_ro(src, anchor + 4u * g.gl);
-					const uint32_t lb = 4u * g.gl;
-					if (lb < lit) o[hl + lb] = (uint8_t)lw;
-					if (lb + 1u < lit) o[hl + lb + 1u] = (uint8_t)(lw >> 8);
-					if (lb + 2u < lit) o[hl + lb + 2u] = (uint8_t)(lw >> 16);
-					if (lb + 3u < lit) o[hl + lb + 3u] = (uint8_t)(lw >> 24);
-					const uint32_t at = g.gl == 0 ? 0u : g.gl == 1 ? 1u : tail + (uint32_t)g.gl - 2u;
-					const uint32_t val = g.gl == 0 ? ((min(lit, 15u) << 4) | min(mc, 15u)) : g.gl == 1 ? lit - 15u
-					    : g.gl == 2 ? off : g.gl == 3 ? off >> 8 : mc - 15u;
-					const bool own = g.gl == 0 || (g.gl == 1 && lit >= 15u) || g.gl == 2 || g.gl == 3 || (g.gl == 4 && mext);
-					if (own) o[at] = (uint8_t)val;
-					op += tail + 2u + mext;
-				} else {
-					if (g.gl == 0) dst[op] = (uint8_t)((min(lit, 15u) << 4) | min(mc, 15u));
-					op++;
-					if (lit >= 15u) op = grp_emit_len(g, dst, op, lit - 15u);
-					grp_copy<true>(g, dst + op, src + anchor, lit);
-					op += lit;
-					if (g.gl == 0) { dst[op] = (uint8_t)off; dst[op + 1] = (uint8_t)(off >> 8); }
-					op += 2;
-					if (mc >= 15u) op = grp_emit_len(g, dst, op, mc - 15u);
-				}
-				anchor = end; shift = 2; g0 = 0;
-				if (end > mflimit) state = GS_TAIL;               // lz4.c:688
-			} else if (enmask != 0xffu) {
-				state = GS_TAIL;                                  // lz4.c:601: search ran into the end margin
-			} else {
-				g0 += LZ4_G;
-			}
-		} else if (state == GS_TAIL) {
-			// ---- last literals (lz4.c:713-729), then the record ----
-			const uint32_t run = n - anchor;
-			if (g.gl == 0) dst[op] = (uint8_t)(min(run, 15u) << 4);
-			op++;
-			if (run >= 15u) op = grp_emit_len(g, dst, op, run - 15u);
-			grp_copy<true>(g, dst + op, src + anchor, run);
-			op += run;
-			if (g.gl == 0) job.lens[idx] = (int32_t)op;
-			if (store) {
-				__syncwarp(g.gmask);
-				grp_commit_record(g, job, idx, sidx, dst, op, (int32_t)op, false);
-			}
-			state = GS_NEW;
-		}
-	}
-}
-
-int launch_fingerprint(const uint8_t *pages, uint64_t stride, uint32_t nbytes, uint32_t n, uint64_t *fps,
-    cudaStream_t st);
 static int g_sm_count = 0;
 int sm_count() {
 	if (!g_sm_count) {
@@ -640,26 +453,6 @@ static int env_int(const char *name, int dflt, int lo, int hi) {
 	return x < lo ? lo : x > hi ? hi : x;
 }
 
-// Launches the 8-lane-group kernel on `st`.  `zero_work` = 0 when another kernel shares the
-// chunk counter.  `ctas_per_sm` bounds the chunks in flight (each owns a 16 KiB global table).
-static int launch_encode_groups(const EncodeJob &job_in, cudaStream_t st, bool zero_work, int ctas_per_sm) {
-	EncodeJob job = job_in;
-	const uint32_t threads = 128, groups_per_cta = threads / LZ4_G;
-	static uint8_t *gtab[64] = {nullptr};
-	int dev = 0;
-	CMB_CHECK(cudaGetDevice(&dev));
-	const uint32_t max_ctas = (uint32_t)sm_count() * (uint32_t)ctas_per_sm;
-	if (!gtab[dev & 63]) CMB_CHECK(cudaMalloc(&gtab[dev & 63], (size_t)sm_count() * 6 * groups_per_cta * LZ4_TABLE_BYTES));
-	job.gtab = gtab[dev & 63];
-	uint32_t grid = (job.n + groups_per_cta - 1) / groups_per_cta;
-	if (grid > max_ctas) grid = max_ctas;
-	if (zero_work) CMB_CHECK(cudaMemsetAsync(job.work, 0, sizeof(unsigned int), st));
-	if (job.nbytes >= LZ4_NARROW_LIMIT) k_encode_groups<true><<<grid, threads, 0, st>>>(job);
-	else k_encode_groups<false><<<grid, threads, 0, st>>>(job);
-	CMB_CHECK(cudaGetLastError());
-	return 0;
-}
-
 template <class K>
 static int launch_encode_kernel(K kern, const EncodeJob &job, int warps, int ctas_per_sm, size_t smem, cudaStream_t st) {
 	CMB_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -676,16 +469,15 @@ static int launch_encode_kernel(K kern, const EncodeJob &job, int warps, int cta
 
 // Plain organisation: residency is bounded by shared memory, one 16 KiB position table per chunk,
 // 14 of them in the 227 KiB of an SM (2 CTAs x 7 warps); chunks handed out dynamically.
-template <int ENC>
 static int launch_encode_warps(const EncodeJob &job, cudaStream_t st, bool fpna) {
 	static int warps = env_int("CMB200_ENC_WARPS", ENC_PLAIN_WARPS, 1, ENC_PLAIN_WARPS);
 	static int ctas = env_int("CMB200_ENC_CTAS_PER_SM", 2, 1, 2);
 	const size_t smem = (size_t)warps * LZ4_TABLE_BYTES;
 	const bool wide = job.nbytes >= LZ4_NARROW_LIMIT;
-	if (wide) return fpna ? launch_encode_kernel(k_encode<true, ENC, true>, job, warps, ctas, smem, st)
-	                      : launch_encode_kernel(k_encode<true, ENC, false>, job, warps, ctas, smem, st);
-	return fpna ? launch_encode_kernel(k_encode<false, ENC, true>, job, warps, ctas, smem, st)
-	            : launch_encode_kernel(k_encode<false, ENC, false>, job, warps, ctas, smem, st);
+	if (wide) return fpna ? launch_encode_kernel(k_encode<true, 0, true>, job, warps, ctas, smem, st)
+	                      : launch_encode_kernel(k_encode<true, 0, false>, job, warps, ctas, smem, st);
+	return fpna ? launch_encode_kernel(k_encode<false, 0, true>, job, warps, ctas, smem, st)
+	            : launch_encode_kernel(k_encode<false, 0, false>, job, warps, ctas, smem, st);
 }
 
 // Ring organisation (lz4_encode_ring.cuh): table + 1 KiB TMA ring + mbarriers per warp, 13 chunks
@@ -702,32 +494,20 @@ static int launch_encode_ring(const EncodeJob &job, cudaStream_t st, bool fpna) 
 
 int launch_encode(const EncodeJob &job_in, cudaStream_t st) {
 	if (job_in.n == 0) return 0;
-	// Two organisations of the same encoder (identical output).
-	//   0 "warps":  one warp per chunk, position table in shared memory — lowest latency per
-	//               chunk, 14 chunks per SM.  Default: best on mixed batches and small launches.
-	//   2 "ring":   "warps" with the parse frontier staged in a per-warp shared-memory ring by TMA
-	//               (lz4_encode_ring.cuh), 13 chunks per SM.  Default.
-	//   1 "groups": one 8-lane group per chunk, table in global memory, 96 chunks per SM — bound by
-	//               L2/HBM latency instead of shared-memory residency; ~15 % faster on match-heavy
-	//               pages in 16 Ki-chunk launches, slower on incompressible ones and small launches.
-	// Running both at once on one batch (shared chunk counter, two streams) was measured too: the
-	// SM does not add the two up (profiles/r1_encode_notes.md).
-	static int mode = env_int("CMB200_ENC_MODE", 2, 0, 3);
-	static int grp_ctas = env_int("CMB200_GRP_CTAS_PER_SM", 6, 1, 6);
+	// One encoder loop (lz4_encode_lean), two data paths with identical output:
+	//   2 "ring" (default): the parse frontier staged in a per-warp shared-memory ring by TMA
+	//               (lz4_encode_ring.cuh), 13 chunks per SM in one CTA;
+	//   0 "plain":  the page read through the L1, 14 chunks per SM — also what accelerations above
+	//               12 and unaligned page buffers use.
+	static int mode = env_int("CMB200_ENC_MODE", 2, 0, 2);
 	static int fpna = env_int("CMB200_FP_NOALLOC", 1, 0, 1);
 	EncodeJob job = job_in;
-	if (mode == 1) {
-		// the fingerprint is fused into the warp kernel; the group kernel takes it from a pass before
-		if (job.fps && launch_fingerprint(job.pages, job.page_stride, job.nbytes, job.n, job.fps, st)) return -1;
-		return launch_encode_groups(job, st, true, grp_ctas);
-	}
 	CMB_CHECK(cudaMemsetAsync(job.work, 0, sizeof(unsigned int), st));
 	// the ring holds what 30 probes at accel <= 12 reach and TMA wants 16-byte aligned pages
 	const bool ring_ok = job.accel >= 1 && job.accel <= RING_MAX_ACCEL && job.nbytes < (1u << 24) &&
 	    (reinterpret_cast<uintptr_t>(job.pages) & 15u) == 0 && (job.page_stride & 15u) == 0;
 	if (mode == 2 && ring_ok) return launch_encode_ring(job, st, fpna != 0);
-	if (mode == 3) return launch_encode_warps<2>(job, st, fpna != 0);      // the round-1 loop
-	return launch_encode_warps<0>(job, st, fpna != 0);
+	return launch_encode_warps(job, st, fpna != 0);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -82,7 +82,6 @@ struct EncodeJob {
 	unsigned long long *rec_out; // out, optional: arena offset of the stored record per chunk (~0 = dropped)
 	uint64_t *fps;           // out, optional: 2 x u64 per chunk {hi, lo}
 	unsigned int *work;      // dynamic work counter (zeroed by the launcher)
-	uint8_t *gtab;           // group encoder: global position tables, set by the launcher
 	// store mode (all null/0 for codec-only use)
 	const uint32_t *slot_idx; // per chunk, from the upsert kernel; 0xffffffff = invalid address
 	const unsigned long long *addr; // per chunk {u,l}

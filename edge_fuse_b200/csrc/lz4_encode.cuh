@@ -1,4 +1,5 @@
-// lz4_encode.cuh — byte-exact LZ4 1.8.1 block encoder, one warp per chunk (sm_100a).
+// lz4_encode.cuh — byte-exact LZ4 1.8.1 block encoder, one warp per chunk (sm_100a): tables, probe
+// neighbourhoods and the out-of-line paths; the loop is lz4_encode_lean in lz4_encode_ring.cuh.
 //
 // Emits exactly the bytes the reference's filemap_set stores:
 //   LZ4_compress_fast(page, dst, n, n+1024, accel)            cachemap/filemap.c:124-128
@@ -7,13 +8,11 @@
 //
 // The greedy parse is a serial dependency chain per chunk (every probe reads then writes the
 // position table), so throughput = chunks in flight / latency per LZ4 sequence.
-//   * Chunks in flight: one independent chunk per warp; only the 16 KiB position table lives in
-//     shared memory, 14 chunks per SM.  The page is read from HBM through the read-only L1 path
-//     (ld.global.nc): it is immutable, probes walk it forward and LZ4 candidates are mostly
-//     recent, so the 128-byte lines get reused.  Staging the whole 64 KiB page in shared memory
-//     would cap residency at two chunks per SM; a 2-8 KiB cp.async sliding window per warp was
-//     built and measured slower than spending the same shared memory on more resident chunks
-//     (DESIGN.md §4).
+//   * Chunks in flight: one independent chunk per warp; the 16 KiB position table lives in shared
+//     memory (13-14 chunks per SM) and, by default, a 1 KiB window of the page at the parse
+//     frontier, kept filled by TMA (lz4_encode_ring.cuh); candidates are read through the
+//     read-only L1 path (ld.global.nc).  Staging the whole 64 KiB page in shared memory would cap
+//     residency at two chunks per SM.
 //   * Latency per sequence: the warp runs the reference's loop speculatively, one LZ4 sequence
 //     per iteration with ONE table round trip and ONE page round trip:
 //       "unified batch": lane 0 replays the table refill of position end-2 (lz4.c:691), lane 1
@@ -240,173 +239,6 @@ __device__ __noinline__ uint32_t lz4_emit_general(uint8_t *dst, uint32_t op, con
 	return op;
 }
 
-// ---- the encoder -----------------------------------------------------------------------------
-
-// Encodes src[0,n) into dst; returns the block length (uniform across the warp).
-// `smem` is this warp's LZ4_TABLE_BYTES of shared memory.  src must be 4-byte aligned and
-// readable up to 16 bytes past src+n (the library's page buffers are contiguous and padded).
-// With FP the EF128 fingerprint of the page is computed along the way (EfFrontier): the parse and
-// the fingerprint then read the page from HBM once, and the stripe loads prefetch the parse.
-template <bool WIDE, bool FP, bool FP_NOALLOC = false>
-__device__ uint32_t lz4_encode_warp(const uint8_t *__restrict__ src, uint32_t n, uint8_t *__restrict__ dst,
-    uint32_t accel, uint8_t *smem, int lane, uint64_t &fp_hi, uint64_t &fp_lo) {
-	Lz4Table<WIDE> tab;
-	tab.t = reinterpret_cast<decltype(tab.t)>(smem);
-	const uint32_t lim4 = (n + 3u) & ~3u;
-	uint32_t op = 0, anchor = 0;
-	EfFrontierT<FP_NOALLOC> fp;
-	if (FP) fp.start(src, n, lane);
-
-	// lz4.c:739 — table cleared per call: an untouched slot aliases position 0.
-	{
-		uint4 z = make_uint4(0, 0, 0, 0);
-		uint4 *t4 = reinterpret_cast<uint4 *>(smem);
-#pragma unroll 4
-		for (uint32_t i = lane; i < LZ4_TABLE_BYTES / 16; i += 32) t4[i] = z;
-	}
-	__syncwarp();
-
-	if (n >= LZ4_MIN_INPUT) {
-		const uint32_t mflimit = n - LZ4_MATCH_FIND_MARGIN;
-		const uint32_t mlimit = n - LZ4_TAIL_LITERALS;
-		// lz4.c:583 stores position 0 under hash(0): a no-op on the cleared table, so skipped.
-		// Per-lane constants of the batch that follows a match ending at `end` (lz4.c:691-710):
-		// lane 0 refills end-2, lane 1 re-tests end, lane j >= 2 is probe k = j-2 of the search
-		// starting at end+1, which runs only while the probe after it stays <= mflimit.
-		const uint32_t kk = (uint32_t)lane - 2u;
-		const int32_t delta2 = lane < 2 ? 2 * lane - 2 : (int32_t)(1u + (kk ? 1u + accel * (kk - 1u) : 0u));
-		const uint32_t need2 = lane < 2 ? 0u : 2u + accel * kk;            // end + need2 <= mflimit
-		// first batch of the chunk: plain search from position 1 (lz4.c:584), no refill / re-test
-		uint32_t shift = 0;          // 2 once a match has ended
-		for (;;) {
-			if (FP) fp.upto(src, anchor + 512u, lane);     // stripes ahead of this batch's probes
-			const bool special = (uint32_t)lane < shift;
-			uint32_t pos;
-			bool en;
-			if (shift) {
-				pos = anchor + (uint32_t)delta2;
-				en = anchor + need2 <= mflimit;
-			} else {
-				pos = 1u + (lane ? 1u + accel * ((uint32_t)lane - 1u) : 0u);
-				en = 2u + accel * (uint32_t)lane <= mflimit;
-			}
-			pos = en ? pos : 0u;                                   // keep disabled lanes' reads in range
-			// speculative literal bytes: src[anchor + lane], src[anchor + 32 + lane] (used when the run is <= 64 bytes)
-			const uint32_t litbyte = ldg8(src + min(anchor + lane, n - 1u));
-			const uint32_t litbyte2 = ldg8(src + min(anchor + 32u + lane, n - 1u));
-
-			// ---- unified batch ----
-			const Lz4Around ai = lz4_around<CMB_LZ4_HINT_PROBE>(src, pos);
-			const uint32_t pseq = ai.at;
-			const uint32_t h = WIDE ? lz4_hash5((uint64_t)ai.at | ((uint64_t)ai.next << 32)) : lz4_hash4(ai.at);
-			const uint32_t cand = tab.get(h);
-			__syncwarp();
-			if (en) tab.put(h, pos);                                // speculative commit
-			__syncwarp();
-			const Lz4Around ac = lz4_around<CMB_LZ4_HINT_CAND>(src, cand);   // latency overlaps the read-back
-			// (Lanes that share a slot store to it in the same instruction: CUDA guarantees that one
-			// of those stores lands; racecheck reports the write-write conflict, it is the mechanism.)
-			const uint32_t seen = tab.get(h);
-			__syncwarp();                                           // read-backs done before any undo store
-			const bool foreign = en && seen != (WIDE ? pos : (pos & 0xffffu));
-			const bool hit = en && !(special && lane == 0) && cand + LZ4_FAR >= pos && ac.at == pseq;
-			const uint32_t foreigns = __ballot_sync(CMB_FULL, foreign);
-			const uint32_t hits = __ballot_sync(CMB_FULL, hit);
-			// match extension known to this lane: up to 4 bytes forward, 4 backward
-			uint32_t nf, nb;
-			{
-				const uint32_t xf = ai.next ^ ac.next;
-				nf = xf ? (uint32_t)(__ffs(xf) - 1) >> 3 : 4u;
-				nf = min(nf, mlimit - min(pos + LZ4_MIN_MATCH, mlimit));
-				const uint32_t xb = ai.before ^ ac.before;
-				nb = xb ? (uint32_t)__clz(xb) >> 3 : 4u;
-				nb = min(nb, min(pos - min(anchor, pos), cand));
-				if (special) nb = 0;                               // the re-test starts a sequence as is
-			}
-			// lanes below the lowest lane that met a foreign value form a dependency-free prefix
-			// (first hit below first foreign lane <=> lowest set bit of `hits` below that of `foreigns`)
-			const uint32_t low_hit = hits & (0u - hits), low_for = foreigns & (0u - foreigns);
-			uint32_t ip, match, fwd, back;
-			bool retest_hit;
-			// one compare: with no hit low_hit - 1 is 0xffffffff (never smaller), with no foreign lane
-			// low_for - 1 is 0xffffffff (any hit is smaller)
-			if (low_hit - 1u < low_for - 1u) {
-				const int w = __ffs(hits) - 1;
-				// put the old value back past the winner, unless the slot now holds the position
-				// of a lane at or before the winner (a committed write that must stay)
-				const uint32_t pos_w = __shfl_sync(CMB_FULL, pos, w);
-				if (en && lane > w && !(foreign && seen <= (WIDE ? pos_w : (pos_w & 0xffffu)))) tab.put(h, cand);
-				__syncwarp();
-				ip = pos_w;
-				match = __shfl_sync(CMB_FULL, cand, w);
-				fwd = __shfl_sync(CMB_FULL, nf, w);
-				back = __shfl_sync(CMB_FULL, nb, w);
-				retest_hit = (uint32_t)w < shift;
-				if (fwd == 4u || back == 4u) {                      // longer than the neighbourhoods show: rare
-					if (fwd == 4u) fwd = 4u + lz4_count_long(src, ip + 8u, match + 8u, mlimit, lim4, lane);
-					if (back == 4u && ip >= anchor + 5u && match >= 5u)
-						back = 4u + lz4_catchup_long(src, ip - 4u, match - 4u, anchor, lane);
-				}
-			} else {
-				uint64_t res = 0;
-				const uint32_t enmask = __ballot_sync(CMB_FULL, en);
-				if (foreigns) {
-					// a lane at or before the first hit depends on an earlier lane of the batch:
-					// undo everything and redo the search in program order
-					if (en) tab.put(h, cand);
-					__syncwarp();
-					res = lz4_search_slow<WIDE>(src, lim4, tab, anchor, shift, accel, mflimit, 0, lane);
-				} else if (enmask == CMB_FULL) {                     // 30 probes were not enough
-					res = lz4_search_slow<WIDE>(src, lim4, tab, anchor, shift, accel, mflimit, 32, lane);
-				}
-				if (!(res >> 63)) break;                             // -> last literals
-				retest_hit = (res >> 62) & 1u;
-				ip = (uint32_t)(res >> 32) & 0x3fffffffu;
-				match = (uint32_t)res;
-				fwd = lz4_count_long(src, ip + LZ4_MIN_MATCH, match + LZ4_MIN_MATCH, mlimit, lim4, lane);
-				back = retest_hit ? 0u : lz4_catchup_long(src, ip, match, anchor, lane);
-			}
-			const uint32_t off = ip - match;
-			const uint32_t mc = back + fwd;               // lz4.c:660 matchCode
-			const uint32_t lit = ip - back - anchor;
-			const uint32_t end = ip + LZ4_MIN_MATCH + fwd;
-
-			// ---- emit: token, literal run (lz4.c:625-641), offset + match length (lz4.c:643-683) ----
-			if (lit <= 64u && mc < 15u + 255u) {
-				uint8_t *o = dst + op;
-				const uint32_t lext = lit >= 15u, mext = mc >= 15u;
-				const uint32_t hl = 1u + lext;
-				if ((uint32_t)lane < lit) o[hl + lane] = (uint8_t)litbyte;
-				if ((uint32_t)lane + 32u < lit) o[hl + 32u + lane] = (uint8_t)litbyte2;
-				// lanes 0-4 each own one of the bytes around the literals: token, literal length
-				// byte, offset low, offset high, match length byte (no branches: byte `lane` of a
-				// packed word, written if the lane's bit of `owners` is set)
-				const uint32_t tail = hl + lit;
-				const uint32_t head4 = (min(lit, 15u) << 4) | min(mc, 15u) | (((lit - 15u) & 0xffu) << 8) | (off << 16);
-				const uint32_t val = lane < 4 ? head4 >> (8u * (uint32_t)lane) : mc - 15u;
-				const uint32_t at = lane < 2 ? (uint32_t)lane : tail + (uint32_t)lane - 2u;
-				const uint32_t owners = 0x0du | (lext << 1) | (mext << 4);
-				if ((owners >> lane) & 1u) o[at] = (uint8_t)val;
-				op += tail + 2u + mext;
-			} else {
-				op = lz4_emit_general(dst, op, src, anchor, lit, off, mc, lane);
-			}
-
-			anchor = end;
-			shift = 2;
-			if (end > mflimit) break;                     // lz4.c:688
-		}
-	}
-
-	// ---- last literals (lz4.c:713-729) ----
-	uint32_t run = n - anchor;
-	if (lane == 0) dst[op] = (uint8_t)(min(run, 15u) << 4);
-	op++;
-	if (run >= 15u) op = lz4_emit_len(dst, op, run - 15u, lane);
-	lz4_copy_literals(dst + op, src + anchor, run, lane);
-	op += run;
-	if (FP) fp.finish(src, n, lane, fp_hi, fp_lo);
-	return op;
-}
+// The encoder loop itself is lz4_encode_lean (lz4_encode_ring.cuh).
 
 }  // namespace cmb

@@ -1,7 +1,7 @@
 // lz4_encode_ring.cuh — the warp-per-chunk LZ4 1.8.1 encoder of lz4_encode.cuh with the page's
 // sliding window staged in shared memory by TMA (sm_100a: cp.async.bulk + mbarrier).
 //
-// Same output bytes as lz4_encode_warp (cachemap/lz4.c:532-733 behind filemap.c:124-128); what
+// Output bytes: LZ4_compress_fast of the reference (cachemap/lz4.c:532-733 behind filemap.c:124-128); what
 // changes is where the parse frontier reads the page from.  Profile of the plain kernel (round 1,
 // T-class pages): 46 % of the stall samples are long-scoreboard waits on the two dependent page
 // reads of a batch — the probe neighbourhoods (30 lanes x 12 bytes spread over ~350 bytes ahead of
@@ -120,7 +120,7 @@ __device__ __noinline__ uint64_t ring_advance(uint32_t s_bytes, uint32_t s_bar, 
 		for (uint32_t g = issued; g < want; g++) {
 			const uint32_t r = g & (RING_BUFS - 1u);
 			// whole 16-byte units; the last buffer of a ragged page reads < 16 bytes past its end
-			// (page buffers are padded, lz4_encode_warp's contract)
+			// (page buffers are padded: src is readable up to 16 bytes past src + n)
 			const uint32_t nb = min(RING_BUF, (n - g * RING_BUF + 15u) & ~15u);
 			const uint8_t *from = src + (size_t)g * RING_BUF;
 			mbar_expect_tx(s_bar + 8u * r, nb + (r == 0u ? RING_MIRROR : 0u));
@@ -157,8 +157,11 @@ __device__ __forceinline__ Lz4Around ring_around(const uint8_t *ring, uint32_t p
 	return r;
 }
 
-// Encodes src[0,n) into dst; returns the block length (uniform across the warp).  Same contract as
-// lz4_encode_warp.  RING: the probe neighbourhoods and literal bytes come from the warp's TMA ring
+// Encodes src[0,n) into dst; returns the block length (uniform across the warp).  tab_smem = this
+// warp's LZ4_TABLE_BYTES of shared memory; src must be 4-byte aligned and readable up to 16 bytes
+// past src + n (the library's page buffers are contiguous and padded).  With FP the EF128
+// fingerprint of the page is computed along the way (EfFrontier): parse and fingerprint then read
+// the page from HBM once.  RING: the probe neighbourhoods and literal bytes come from the warp's TMA ring
 // (accel <= RING_MAX_ACCEL, src 16-byte aligned, `ring` set up by this warp); otherwise from global
 // memory through the L1.
 // One lane layout for every batch: lane 0 refills the slot of end-2 (lz4.c:691), lane 1 re-tests

@@ -196,10 +196,11 @@ def test_encode_wide_mode_fuzz(E, gpu, oracle):
     assert (used == np.array([len(b) for b in blocks])).all() and (out == np.stack(ps)).all()
 
 
-def test_group_encoder_mode_parity(gpu):
-    """The alternative encoder organisation (CMB200_ENC_MODE=1: 8 lanes per chunk, position tables
-    in global memory) must emit the same bytes; the mode is read once per process, so it runs in
-    a child process over the golden vectors and a slice of the fuzz set."""
+def test_plain_data_path_parity(gpu):
+    """The encoder's other data path (CMB200_ENC_MODE=0: the page read through the L1 instead of the
+    TMA ring — what accelerations above 12 and unaligned buffers take) must emit the same bytes; the
+    mode is read once per process, so it runs in a child process over the golden vectors and a
+    slice of the fuzz set."""
     import subprocess
     import sys
     code = r'''
@@ -227,12 +228,12 @@ eng.put(u, l, pages); out, st = eng.get(u, l)
 assert (st == E.HIT).all() and (out == pages).all()
 fps, ok = eng.read_fingerprints(u, l)
 assert ok.all() and (int(fps[5, 0]), int(fps[5, 1])) == O.fingerprint128(pages[5])
-print("group-mode parity ok")
+print("plain-path parity ok")
 '''
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, CMB200_ENC_MODE="1"),
+    out = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, CMB200_ENC_MODE="0"),
                          capture_output=True, text=True, timeout=600)
-    assert out.returncode == 0 and "group-mode parity ok" in out.stdout, out.stdout + out.stderr
+    assert out.returncode == 0 and "plain-path parity ok" in out.stdout, out.stdout + out.stderr
 
 
 @pytest.mark.gpu
