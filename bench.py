@@ -114,6 +114,54 @@ def workload_config(gpus: int, chunks: int) -> dict:
 # reference / CPU arm  (imports oracle/ only — never the product library)
 # -------------------------------------------------------------------------------------------------
 
+def reference_store_child(n: int, threads: int) -> int:
+    """(child process of reference_store_rates) cachemap_put / cachemap_get of the reference's own
+    library over the first n chunks of the stream, `threads` pthreads, LMDB on tmpfs; one JSON line."""
+    import ctypes as C
+    import tempfile
+    from oracle import ef_oracle as O
+    L, R = O.lib(), O.ref()
+    cids = np.arange(n, dtype=np.uint64)
+    pages = O.gen_chunks(SEED, cids, CHUNK, threads)
+    off, nh = O.gen_addr(SEED, cids, PSHIFT)
+    offs = np.ascontiguousarray(off, dtype=np.uint64)
+    nhs = np.ascontiguousarray(nh, dtype=np.uint64)
+    out3 = (C.c_double * 3)()
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    with tempfile.TemporaryDirectory(dir=base) as d:
+        cm = R.cachemap_create(d.encode(), max(1024, 2 * n), ACCEL, PSHIFT)
+        assert cm, "reference cachemap_create failed"
+        L.ef_cpu_bench_store(C.cast(R.cachemap_put, C.c_void_p), C.cast(R.cachemap_get, C.c_void_p),
+                             C.c_void_p(cm), pages.ctypes.data, n, CHUNK, offs.ctypes.data,
+                             nhs.ctypes.data, threads, 1, out3)
+        assert out3[2] == 0, "reference get returned different bytes"
+        print(json.dumps({"put_gibs": n * CHUNK / GIB / out3[0], "get_gibs": n * CHUNK / GIB / out3[1]}), flush=True)
+        # no cachemap_free(): it can hang in the reference (SURVEY.md §5); the process just ends and the
+        # LMDB files go away with the temporary directory
+        sys.stdout.flush()
+        os._exit(0)
+
+
+def reference_store_rates(n: int, threads: int) -> dict:
+    """The reference's full put / get path over the first n chunks, measured in a child process under
+    a watchdog: cachemap_create starts its put threads before it initialises the mutex and condition
+    variable they use (cachemap.c:123-138), and a process that loses that race sleeps forever before
+    the first put (seen in ~3 % of the starts on the 128-thread GPU host, in half of them on a small
+    one).  Such a child is killed and the measurement repeated; the numbers come from a run that ran."""
+    import subprocess
+    limit = 90 + 60 * n // 16384
+    for attempt in range(5):
+        try:
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--ref-store-child", str(n), str(threads)],
+                                 capture_output=True, text=True, timeout=limit)
+        except subprocess.TimeoutExpired:
+            continue
+        lines = [x for x in out.stdout.splitlines() if x.startswith("{")]
+        assert out.returncode == 0 and lines, f"reference store run failed: {out.stdout[-300:]} {out.stderr[-600:]}"
+        return json.loads(lines[-1])
+    raise RuntimeError("the reference library hung at start-up in five attempts")
+
+
 def cpu_reference_run(pages: np.ndarray, off: np.ndarray, nh: np.ndarray, threads: int, codec: bool = True):
     """Times the reference's CPU path on `pages` ([n, 65536] host array).  Returns a dict with the
     full-path put/get rate (cachemap_put / cachemap_get on a tmpfs store) and, with codec=True, the
@@ -136,21 +184,7 @@ def cpu_reference_run(pages: np.ndarray, off: np.ndarray, nh: np.ndarray, thread
         res.update({"codec_encode_gibs": n * CHUNK / GIB / out4[0], "codec_decode_gibs": n * CHUNK / GIB / out4[1],
                     "ratio": out4[3] / (n * CHUNK)})
     if R is not None:
-        base = "/dev/shm" if os.path.isdir("/dev/shm") else None
-        out3 = (C.c_double * 3)()
-        offs = np.ascontiguousarray(off, dtype=np.uint64)
-        nhs = np.ascontiguousarray(nh, dtype=np.uint64)
-        with tempfile.TemporaryDirectory(dir=base) as d:
-            cm = R.cachemap_create(d.encode(), max(1024, 2 * n), ACCEL, PSHIFT)
-            assert cm, "reference cachemap_create failed"
-            L.ef_cpu_bench_store(C.cast(R.cachemap_put, C.c_void_p), C.cast(R.cachemap_get, C.c_void_p),
-                                 C.c_void_p(cm), pages.ctypes.data, n, CHUNK, offs.ctypes.data,
-                                 nhs.ctypes.data, threads, 1, out3)
-            assert out3[2] == 0, "reference get returned different bytes"
-            # no cachemap_free(): it can hang in the reference; the LMDB files go
-            # away with the temporary directory
-        res["put_gibs"] = n * CHUNK / GIB / out3[0]
-        res["get_gibs"] = n * CHUNK / GIB / out3[1]
+        res.update(reference_store_rates(n, threads))
     return res
 
 
@@ -695,6 +729,8 @@ def run_ours(args):
 
 
 def main():
+    if len(sys.argv) == 4 and sys.argv[1] == "--ref-store-child":     # see reference_store_rates
+        return reference_store_child(int(sys.argv[2]), int(sys.argv[3]))
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
