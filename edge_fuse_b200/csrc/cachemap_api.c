@@ -97,6 +97,7 @@ struct filemap {
 	uint64_t wb_n, wb_head, wb_tail;
 	pthread_t wb_thread;
 	int wb_started, wb_stop;
+	int wb_flusher_asleep;  /* the flusher waits on wb_work (under wb_mu) */
 	/* persistence: <destdir>/cachemap_b200.snap (cmb200_save / cmb200_load) */
 	int persist;
 	long checkpoint_sec;    /* > 0: the flusher saves a snapshot this often when puts have arrived */
@@ -412,7 +413,9 @@ filemap_flusher(void *arg)
 	pthread_mutex_lock(&m->wb_mu);
 	for (;;) {
 		uint64_t count = 0;
-		while (m->wb_tail + count < m->wb_head && count < FLUSH_MAX &&
+		/* at most half the ring per batch: callers keep filling the other half while this one is on the GPU */
+		const uint64_t flush_cap = m->wb_n / 2 < FLUSH_MAX ? (m->wb_n / 2 ? m->wb_n / 2 : 1) : FLUSH_MAX;
+		while (m->wb_tail + count < m->wb_head && count < flush_cap &&
 		    m->wb_slot[(m->wb_tail + count) % m->wb_n].state == WB_READY)
 			count++;
 		if (count == 0) {
@@ -430,9 +433,13 @@ filemap_flusher(void *arg)
 				}
 				until = now;
 				until.tv_sec += 1;
+				m->wb_flusher_asleep = 1;
 				pthread_cond_timedwait(&m->wb_work, &m->wb_mu, &until);
+				m->wb_flusher_asleep = 0;
 			} else {
+				m->wb_flusher_asleep = 1;
 				pthread_cond_wait(&m->wb_work, &m->wb_mu);
+				m->wb_flusher_asleep = 0;
 			}
 			continue;
 		}
@@ -694,7 +701,8 @@ filemap_set(struct filemap *m, uint128_t *key, void *value, uint64_t attr)
 	memcpy(m->wb_pages + (s % m->wb_n) * (size_t)m->bsize, value, (size_t)m->bsize);
 	pthread_mutex_lock(&m->wb_mu);
 	w->state = WB_READY;
-	pthread_cond_signal(&m->wb_work);
+	if (m->wb_flusher_asleep)               /* a busy flusher finds the page by itself when it comes back: no wake-up call per put */
+		pthread_cond_signal(&m->wb_work);
 	pthread_mutex_unlock(&m->wb_mu);
 }
 
