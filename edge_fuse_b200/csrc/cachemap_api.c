@@ -42,7 +42,7 @@
 #ifndef GET_CALLERS
 #define GET_CALLERS 32          /* callers inside the combining queue at once; the rest sleep at its door */
 #endif
-#define FLUSH_MAX 1024          /* pages the flusher hands over per GPU batch */
+#define FLUSH_MAX 4096          /* pages the flusher hands over per GPU batch */
 #define PNUM_SHIFT 44           /* cachemap.c:155 */
 
 enum req_kind { REQ_GET, REQ_UNSET };
@@ -142,8 +142,10 @@ filemap_engine_ready(struct filemap *m)
 		m->eng = cmb200_engine_create(&cfg);
 		if (m->eng) {
 			m->h_stage = cmb200_host_alloc((size_t)LEADERS * COMBINE_MAX * m->bsize);
-			/* ring of ~64 MiB by default, at least 64 pages */
-			long slots = env_long("CMB200_WB_SLOTS", (64L << 20) / m->bsize);
+			/* ring of 256 MiB by default, at least 64 pages.  The size sets the batch the flusher can form
+			 * (half the ring), and a batch below ~2 000 chunks leaves the encode kernel a partial wave
+			 * whose duration is one chunk's latency (~2 ms for a text-like page) whatever its size */
+			long slots = env_long("CMB200_WB_SLOTS", (256L << 20) / m->bsize);
 			if (slots > 0 && slots < 64)
 				slots = 64;
 			if (slots > 0) {
