@@ -622,12 +622,12 @@ filemap_submit_many(struct filemap *m, struct fm_req *reqs, int count)
 				continue;
 			}
 			pthread_mutex_lock(&m->q_mu);
-			if (!r->status && !m->launching) {
+			if (!r->status && !__atomic_load_n(&m->launching, __ATOMIC_RELAXED)) {
 				int ls = -1;
 				for (int k = 0; k < LEADERS; k++)
 					if (!m->leader_busy[k]) { ls = k; break; }
 				if (ls >= 0) {
-					m->launching = 1;
+					__atomic_store_n(&m->launching, 1, __ATOMIC_RELAXED);  /* (read by watchers that hold no lock) */
 					m->leader_busy[ls] = 1;
 					__atomic_fetch_add(&m->busy_slots, 1, __ATOMIC_RELAXED);
 					filemap_lead(m, ls);                    /* (drops and retakes q_mu around the launch) */
@@ -640,14 +640,14 @@ filemap_submit_many(struct filemap *m, struct fm_req *reqs, int count)
 
 		/* my answer: the kernel writes the page, fences, then the status word */
 		int32_t st;
-		for (unsigned spins = 0; (st = *answer) == CMB200_SMALL_PENDING; spins++) {
+		for (unsigned spins = 0; (st = __atomic_load_n(answer, __ATOMIC_ACQUIRE)) == CMB200_SMALL_PENDING; spins++) {
 #if defined(__x86_64__)
 			__builtin_ia32_pause();
 #endif
 			if ((spins & 4095u) == 4095u)
 				sched_yield();
 		}
-		__atomic_thread_fence(__ATOMIC_ACQUIRE);
+		/* (the acquire load above orders the page bytes after the status word) */
 		if (r->kind == REQ_GET) {
 			if (st == CMB200_HIT) {
 				r->out = r->dst ? r->dst : malloc((size_t)m->bsize);    /* filemap.c:242 */
