@@ -22,10 +22,10 @@ def _build(tmp_path, name, extra):
     return exe if r.returncode == 0 else None, r.stderr
 
 
-def _run(exe, threads, ops, pshift, limit):
+def _run(exe, threads, ops, pshift, limit, **extra_env):
     d = tempfile.mkdtemp()
     try:
-        env = dict(os.environ, CMB200_PERSIST="0", TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0")
+        env = dict(os.environ, CMB200_PERSIST="0", TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0", **extra_env)
         return subprocess.run([exe, d, str(threads), str(ops), str(pshift), str(limit)], capture_output=True, text=True,
                               timeout=limit + 30, env=env)
     finally:
@@ -39,6 +39,17 @@ def test_host_layer_under_many_callers(tmp_path, threads, pshift):
     exe, err = _build(tmp_path, "host_stress", [])
     assert exe, err
     out = _run(exe, threads, 1500 if pshift == 12 else 400, pshift, 150)
+    assert out.returncode == 0 and "host_stress ok" in out.stdout, out.stdout + out.stderr
+
+
+@pytest.mark.parametrize("slots,pshift,threads", [("64", 12, 24), ("64", 16, 12), ("0", 12, 12), ("256", 17, 8)])
+def test_host_layer_ring_shapes_and_large_pages(tmp_path, slots, pshift, threads):
+    """A write-behind ring of 64 slots (wrap-around and back-pressure all the time), no ring at all
+    (synchronous puts), and 128 KiB pages, which the fused single-page get does not serve: the queue
+    then answers its batches through the synchronous two-kernel call."""
+    exe, err = _build(tmp_path, "host_stress", [])
+    assert exe, err
+    out = _run(exe, threads, 1200 if pshift < 16 else 300, pshift, 150, CMB200_WB_SLOTS=slots)
     assert out.returncode == 0 and "host_stress ok" in out.stdout, out.stdout + out.stderr
 
 
