@@ -8,7 +8,7 @@
  *   - every call returns (the combining queue loses no request): the run ends, a watchdog aborts it
  *     otherwise;
  *   - requests / hits counters add up.
- * usage: host_stress <cachedir> <threads> <ops per thread> <pshift> */
+ * usage: host_stress <cachedir> <threads> <ops per thread> <pshift> [watchdog seconds] [evict] */
 #include <pthread.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -17,6 +17,7 @@
 #include <unistd.h>
 
 #include "../../include/cachemap.h"
+#include "../../include/filemap.h"
 
 static struct cachemap *cm;
 static int threads, ops, pshift;
@@ -95,6 +96,31 @@ static void *worker(void *arg) {
 	return NULL;
 }
 
+/* Eviction mode: far more keys than the capacity.  Nothing can be promised about which keys stay,
+ * only that a page that comes back is whole and its key's, and that the store ends up at capacity. */
+static void *evict_worker(void *arg) {
+	const long t = (long)arg;
+	unsigned seed = 777u + (unsigned)t * 104729u;
+	uint8_t *page = malloc(bsize);
+	long err = 0, g = 0, h = 0;
+	for (int op = 0; op < ops; op++) {
+		const unsigned r = rand_r(&seed);
+		const uint64_t key = 2000000u + (uint64_t)t * 100000u + (r >> 4) % 20000u;
+		if (r & 1) { fill(page, key, (uint64_t)op + 1); cachemap_put(cm, key << pshift, 9, 2, page); }
+		else {
+			uint8_t *p = cachemap_get(cm, key << pshift, 9, 2);
+			g++;
+			if (p) { h++; if (check(p, key) < 0) err++; }
+			free(p);
+		}
+	}
+	__atomic_fetch_add(&errors, err, __ATOMIC_RELAXED);
+	__atomic_fetch_add(&gets_done, g, __ATOMIC_RELAXED);
+	__atomic_fetch_add(&hits_done, h, __ATOMIC_RELAXED);
+	free(page);
+	return NULL;
+}
+
 static void *watchdog(void *arg) {
 	sleep((unsigned)(uintptr_t)arg);
 	fprintf(stderr, "host_stress: watchdog — calls did not return in time\n");
@@ -108,11 +134,13 @@ int main(int argc, char **argv) {
 	bsize = (size_t)1 << pshift;
 	pthread_t wd;
 	pthread_create(&wd, NULL, watchdog, (void *)(uintptr_t)(argc > 5 ? atoi(argv[5]) : 120));
-	cm = cachemap_create(argv[1], 1 << 15, 12, pshift);
+	const int evict = argc > 6 && strcmp(argv[6], "evict") == 0;
+	const uint64_t capacity = evict ? 2048 : 1 << 15;
+	cm = cachemap_create(argv[1], capacity, 12, pshift);
 	if (!cm) { fprintf(stderr, "cachemap_create failed\n"); return 1; }
 	pthread_t th[256];
 	if (threads > 256) threads = 256;
-	for (long t = 0; t < threads; t++) pthread_create(&th[t], NULL, worker, (void *)t);
+	for (long t = 0; t < threads; t++) pthread_create(&th[t], NULL, evict ? evict_worker : worker, (void *)t);
 	for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);
 	uint64_t rq = 0, ht = 0;
 	cachemap_get_counters(cm, &rq, &ht);
@@ -121,6 +149,13 @@ int main(int argc, char **argv) {
 	int bad = errors != 0;
 	/* single gets are counted one by one; the range reads add requests of their own (at most one per page) */
 	if ((long)rq < gets_done || (long)rq > gets_done + range_pages || (long)ht < hits_done) { fprintf(stderr, "counters do not add up\n"); bad = 1; }
+	if (evict) {
+		/* eviction runs before every batch of the flusher: what is left over is at most the capacity
+		 * (cachemap.c:17-45), and the cache did fill up */
+		const uint64_t left = filemap_entries(*(struct filemap **)cm);     /* `pages` is the first member (cachemap.h:20-21) */
+		printf("entries %lu capacity %lu\n", (unsigned long)left, (unsigned long)capacity);
+		if (left > capacity || left < capacity / 2) { fprintf(stderr, "entries out of bounds\n"); bad = 1; }
+	}
 	cachemap_free(cm);
 	printf(bad ? "host_stress FAILED\n" : "host_stress ok\n");
 	return bad;

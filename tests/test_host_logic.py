@@ -22,11 +22,11 @@ def _build(tmp_path, name, extra):
     return exe if r.returncode == 0 else None, r.stderr
 
 
-def _run(exe, threads, ops, pshift, limit, **extra_env):
+def _run(exe, threads, ops, pshift, limit, *mode, **extra_env):
     d = tempfile.mkdtemp()
     try:
         env = dict(os.environ, CMB200_PERSIST="0", TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0", **extra_env)
-        return subprocess.run([exe, d, str(threads), str(ops), str(pshift), str(limit)], capture_output=True, text=True,
+        return subprocess.run([exe, d, str(threads), str(ops), str(pshift), str(limit), *mode], capture_output=True, text=True,
                               timeout=limit + 30, env=env)
     finally:
         shutil.rmtree(d, ignore_errors=True)
@@ -50,6 +50,17 @@ def test_host_layer_ring_shapes_and_large_pages(tmp_path, slots, pshift, threads
     exe, err = _build(tmp_path, "host_stress", [])
     assert exe, err
     out = _run(exe, threads, 1200 if pshift < 16 else 300, pshift, 150, CMB200_WB_SLOTS=slots)
+    assert out.returncode == 0 and "host_stress ok" in out.stdout, out.stdout + out.stderr
+
+
+@pytest.mark.parametrize("threads", [1, 16])
+def test_host_layer_keeps_capacity_under_eviction(tmp_path, threads):
+    """Ten times more keys than the capacity: the flusher evicts before every batch
+    (cachemap.c:17-45 as filemap_evict), pages that come back are whole and their key's, and the store
+    ends at its capacity."""
+    exe, err = _build(tmp_path, "host_stress", [])
+    assert exe, err
+    out = _run(exe, threads, 4000, 12, 150, "evict")
     assert out.returncode == 0 and "host_stress ok" in out.stdout, out.stdout + out.stderr
 
 
