@@ -149,7 +149,7 @@ def reference_store_rates(n: int, threads: int) -> dict:
     the first put (seen in ~3 % of the starts on the 128-thread GPU host, in half of them on a small
     one).  Such a child is killed and the measurement repeated; the numbers come from a run that ran."""
     import subprocess
-    limit = 90 + 60 * n // 16384
+    limit = 40 + 30 * n // 16384                          # a healthy child needs a few seconds even for the whole 1 GiB step
     for attempt in range(5):
         try:
             out = subprocess.run([sys.executable, os.path.abspath(__file__), "--ref-store-child", str(n), str(threads)],
